@@ -1,0 +1,547 @@
+/*
+ * hb_api.cu -- the C ABI of libhuffb200.so (see include/huffman_b200.h).
+ *
+ * Mirrors the five-step sequence of the reference's runVLCTest (main_test_cu.cu:52-180):
+ *   init -> histogram (hist.cu) -> codebook (huffTree.h, load_data.h:40-47)
+ *        -> encode (vlc_kernel_sm64huff.cu + scan.cu + pack_kernels.cu) -> free
+ * with caller-owned data buffers, explicit streams, error codes instead of exit(), and no hidden
+ * globals (the reference keeps scan scratch in file-scope statics, scan.cu:63-65).
+ * There is no CPU fallback anywhere in this file.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+
+#include "../../include/huffman_b200.h"
+#include "hb_kernels.cuh"
+
+struct hb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t max_words = 0;
+    uint64_t max_tiles = 0;
+
+    unsigned long long *d_desc = nullptr;     // look-back descriptors, one per tile
+    unsigned long long *d_ticket = nullptr;   // monotonically increasing tile ticket
+    uint64_t ticket_base = 0;
+    uint32_t epoch = 0;
+
+    uint32_t *d_table = nullptr;              // 512 words: packed[256] or wide uint2[256]
+    uint32_t *h_table = nullptr;              // pinned staging for the table upload
+    cudaEvent_t table_uploaded = nullptr;
+    uint32_t cw_cache[256];
+    uint32_t len_cache[256];
+    bool table_valid = false;
+    hb::EncVariant variant = hb::kPackedG1;
+
+    hb::EncResult *h_result = nullptr;        // mapped pinned; the kernel writes it directly
+    uint64_t pending_start_bit = 0;
+    bool pending = false;
+    bool pending_empty = false;
+
+    unsigned long long *d_hist = nullptr;     // 256 bins
+    uint32_t *d_thr = nullptr;                // synth: thresholds
+    uint8_t *d_symmap = nullptr;
+
+    // host-buffer pipeline (hb_vlc_encode_host)
+    uint32_t *d_in_buf = nullptr;
+    uint64_t in_buf_words = 0;
+    uint32_t *d_out_buf = nullptr;
+    uint64_t out_buf_words = 0;
+    cudaStream_t s_main = nullptr;
+    cudaStream_t s_d2h = nullptr;
+    cudaEvent_t ev_chunk = nullptr;
+
+    uint64_t launches = 0;
+    int last_cuda = 0;
+};
+
+namespace {
+
+int cuda_fail(hb_ctx *ctx, cudaError_t e)
+{
+    if (ctx) ctx->last_cuda = (int)e;
+    (void)cudaGetLastError();   // clear the sticky-less error state
+    return HB_ERR_CUDA;
+}
+
+#define HB_CUDA(ctx, call)                                   \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail((ctx), e__); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess) {
+            ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+        } else {
+            ok = cudaSetDevice(dev) == cudaSuccess;
+            prev = -1;
+        }
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) (void)cudaSetDevice(prev);
+    }
+};
+
+// Validate the caller's tables against the parity domain and pack them for the kernel.
+int pack_tables(const uint32_t cw[256], const uint32_t len[256], uint32_t packed[512],
+                hb::EncVariant *variant)
+{
+    uint32_t max_len = 0;
+    for (int s = 0; s < 256; s++) {
+        if (len[s] > HB_MAX_CODE_LEN) return HB_ERR_CODELEN;
+        if (len[s] < 32 && (cw[s] >> len[s]) != 0) return HB_ERR_CODEWORD;
+        if (len[s] > max_len) max_len = len[s];
+    }
+    const hb::EncVariant v = hb::pick_variant((int)max_len);
+    memset(packed, 0, 512 * sizeof(uint32_t));
+    for (int s = 0; s < 256; s++) {
+        const uint32_t l = len[s];
+        const uint32_t left = l ? (cw[s] << (32u - l)) : 0u;
+        if (v == hb::kWideG1) {
+            packed[2 * s] = left;
+            packed[2 * s + 1] = l;
+        } else {
+            packed[s] = left | l;      // l <= 24: the codeword bits sit at or above bit 8
+        }
+    }
+    *variant = v;
+    return HB_OK;
+}
+
+int set_codebook(hb_ctx *ctx, const uint32_t cw[256], const uint32_t len[256], cudaStream_t stream)
+{
+    if (ctx->table_valid && memcmp(cw, ctx->cw_cache, sizeof(ctx->cw_cache)) == 0 &&
+        memcmp(len, ctx->len_cache, sizeof(ctx->len_cache)) == 0)
+        return HB_OK;
+    uint32_t packed[512];
+    hb::EncVariant v;
+    const int rc = pack_tables(cw, len, packed, &v);
+    if (rc != HB_OK) return rc;
+    // the pinned staging block may still be in flight from the previous upload
+    HB_CUDA(ctx, cudaEventSynchronize(ctx->table_uploaded));
+    memcpy(ctx->h_table, packed, sizeof(packed));
+    HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_table, ctx->h_table, sizeof(packed), cudaMemcpyHostToDevice,
+                                 stream));
+    HB_CUDA(ctx, cudaEventRecord(ctx->table_uploaded, stream));
+    memcpy(ctx->cw_cache, cw, sizeof(ctx->cw_cache));
+    memcpy(ctx->len_cache, len, sizeof(ctx->len_cache));
+    ctx->variant = v;
+    ctx->table_valid = true;
+    return HB_OK;
+}
+
+uint64_t tiles_of(uint64_t n_words) { return (n_words + hb::kTileWords - 1) / hb::kTileWords; }
+
+// Launch the encode kernel over tiles [first_tile, end_tile) of a job.
+int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t first_tile,
+                 uint64_t end_tile, uint32_t *d_out, uint64_t cap_words, uint64_t start_bit,
+                 cudaStream_t stream)
+{
+    hb::EncParams p;
+    p.in = d_in;
+    p.n_words = n_words;
+    p.n_tiles = tiles_of(n_words);
+    p.first_tile = first_tile;
+    p.end_tile = end_tile;
+    p.out = d_out;
+    p.out_cap_words = cap_words;
+    p.start_bit = start_bit;
+    p.desc = ctx->d_desc;
+    p.ticket = ctx->d_ticket;
+    p.ticket_base = ctx->ticket_base;
+    p.epoch = ctx->epoch;
+    p.table = ctx->d_table;
+    p.result = ctx->h_result;
+
+    const uint64_t tiles = end_tile - first_tile;
+    int per_sm = hb::encode_max_ctas_per_sm(ctx->variant);
+    if (per_sm < 1) return cuda_fail(ctx, cudaErrorInvalidConfiguration);
+    static const char *env = getenv("HB_CTAS_PER_SM");
+    if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
+    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+    if (grid > tiles) grid = tiles;
+    HB_CUDA(ctx, hb::launch_encode(ctx->variant, p, (int)grid, stream));
+    ctx->ticket_base += tiles + grid;      // every CTA draws exactly one ticket past the end
+    ctx->launches++;
+    return HB_OK;
+}
+
+int next_epoch(hb_ctx *ctx, cudaStream_t stream)
+{
+    ctx->epoch = (ctx->epoch + 1) & hb::kEpochMask;
+    if (ctx->epoch == 0) {
+        // tags wrapped: wipe stale descriptors once every 16383 jobs
+        HB_CUDA(ctx, cudaMemsetAsync(ctx->d_desc, 0, ctx->max_tiles * sizeof(unsigned long long), stream));
+        ctx->epoch = 1;
+    }
+    return HB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_init(hb_ctx **out, int device, uint64_t max_words)
+{
+    if (!out) return HB_ERR_ARG;
+    *out = nullptr;
+    hb_ctx *ctx = new (std::nothrow) hb_ctx();
+    if (!ctx) return HB_ERR_NOMEM;
+    ctx->device = device;
+    memset(ctx->cw_cache, 0, sizeof(ctx->cw_cache));
+    memset(ctx->len_cache, 0, sizeof(ctx->len_cache));
+
+    DeviceGuard g(device);                    // the caller's current device is restored on return
+    cudaError_t e = g.ok ? cudaSuccess : cudaGetLastError();
+    if (e == cudaSuccess && !g.ok) e = cudaErrorInvalidDevice;
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    if (e == cudaSuccess && prop.major < 10) e = cudaErrorNoKernelImageForDevice;   // sm_100a only
+    if (e == cudaSuccess) e = hb::encode_configure();
+    if (e != cudaSuccess) {
+        int rc = cuda_fail(ctx, e);
+        fprintf(stderr, "hb_init: CUDA error %d (%s); libhuffb200 has no CPU fallback\n", (int)e,
+                cudaGetErrorString(e));
+        delete ctx;
+        return rc;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_words = max_words ? max_words : 1;
+    ctx->max_tiles = tiles_of(ctx->max_words) + 1;
+
+    bool ok = true;
+    ok = ok && cudaMalloc(&ctx->d_desc, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_desc, 0, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_table, 512 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMallocHost(&ctx->h_table, 512 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_result, sizeof(hb::EncResult), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_thr, 256 * sizeof(uint32_t)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_symmap, 256) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->table_uploaded, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) {
+        ctx->last_cuda = (int)cudaGetLastError();
+        hb_free(ctx);
+        return HB_ERR_NOMEM;
+    }
+    ctx->h_result->bits_end = 0;
+    ctx->h_result->overflow = 0;
+    *out = ctx;
+    return HB_OK;
+}
+
+void hb_free(hb_ctx *ctx)
+{
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    (void)cudaDeviceSynchronize();
+    cudaFree(ctx->d_desc);
+    cudaFree(ctx->d_ticket);
+    cudaFree(ctx->d_table);
+    if (ctx->h_table) cudaFreeHost(ctx->h_table);
+    if (ctx->h_result) cudaFreeHost(ctx->h_result);
+    cudaFree(ctx->d_hist);
+    cudaFree(ctx->d_thr);
+    cudaFree(ctx->d_symmap);
+    cudaFree(ctx->d_in_buf);
+    cudaFree(ctx->d_out_buf);
+    if (ctx->table_uploaded) cudaEventDestroy(ctx->table_uploaded);
+    if (ctx->ev_chunk) cudaEventDestroy(ctx->ev_chunk);
+    if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    (void)cudaGetLastError();
+    delete ctx;
+}
+
+int hb_histogram_device(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t *d_hist,
+                        void *stream)
+{
+    if (!ctx || !d_hist || (!d_in && n_words) || ((uintptr_t)d_in & 3u)) return HB_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    HB_CUDA(ctx, hb::launch_histogram(d_in, n_words, (unsigned long long *)d_hist, ctx->sm_count,
+                                      (cudaStream_t)stream));
+    if (n_words) ctx->launches++;
+    return HB_OK;
+}
+
+int hb_histogram(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t hist[256], void *stream)
+{
+    if (!ctx || !hist) return HB_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    HB_CUDA(ctx, cudaMemsetAsync(ctx->d_hist, 0, 256 * sizeof(unsigned long long), st));
+    const int rc = hb_histogram_device(ctx, d_in, n_words, (uint64_t *)ctx->d_hist, stream);
+    if (rc != HB_OK) return rc;
+    HB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->d_hist, 256 * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st));
+    HB_CUDA(ctx, cudaStreamSynchronize(st));
+    return HB_OK;
+}
+
+int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const uint32_t codewords[256],
+                    const uint32_t codewordlens[256], uint32_t *d_out, uint64_t out_capacity_words,
+                    uint64_t start_bit, void *stream)
+{
+    if (!ctx || !codewords || !codewordlens || !d_out || (!d_in && n_words)) return HB_ERR_ARG;
+    if (((uintptr_t)d_in & 31u) || ((uintptr_t)d_out & 3u)) return HB_ERR_ARG;
+    if (n_words > ctx->max_words) return HB_ERR_CAPACITY;
+    if (start_bit >> 47) return HB_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = set_codebook(ctx, codewords, codewordlens, st);
+    if (rc != HB_OK) return rc;
+
+    // Several encodes may be queued on the same stream: the kernel only ever SETS result->overflow and
+    // the last launch's last tile writes result->bits_end; the host touches the block in
+    // hb_encode_result only, after the stream has drained.
+    if (n_words == 0) {
+        // cpuencode.cpp:17 -- the first output word is cleared even for an empty input
+        if ((start_bit >> 5) >= out_capacity_words) return HB_ERR_CAPACITY;
+        if ((start_bit & 31u) == 0)
+            HB_CUDA(ctx, cudaMemsetAsync(d_out + (start_bit >> 5), 0, sizeof(uint32_t), st));
+        ctx->pending = true;
+        ctx->pending_empty = true;
+        ctx->pending_start_bit = start_bit;
+        return HB_OK;
+    }
+    if ((rc = next_epoch(ctx, st)) != HB_OK) return rc;
+    rc = launch_tiles(ctx, d_in, n_words, 0, tiles_of(n_words), d_out, out_capacity_words, start_bit, st);
+    if (rc != HB_OK) return rc;
+    ctx->pending = true;
+    ctx->pending_empty = false;
+    ctx->pending_start_bit = start_bit;
+    return HB_OK;
+}
+
+int hb_encode_result(hb_ctx *ctx, uint64_t *total_bits, void *stream)
+{
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->pending) return HB_ERR_STATE;
+    DeviceGuard g(ctx->device);
+    HB_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    ctx->pending = false;
+    const bool overflow = ctx->h_result->overflow != 0;
+    ctx->h_result->overflow = 0;
+    if (total_bits)
+        *total_bits = ctx->pending_empty ? 0 : ctx->h_result->bits_end - ctx->pending_start_bit;
+    return overflow ? HB_ERR_CAPACITY : HB_OK;
+}
+
+int hb_encode(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const uint32_t codewords[256],
+              const uint32_t codewordlens[256], uint32_t *d_out, uint64_t out_capacity_words,
+              uint64_t start_bit, uint64_t *total_bits, void *stream)
+{
+    const int rc = hb_encode_async(ctx, d_in, n_words, codewords, codewordlens, d_out,
+                                   out_capacity_words, start_bit, stream);
+    if (rc != HB_OK) return rc;
+    return hb_encode_result(ctx, total_bits, stream);
+}
+
+// ---- host-buffer pipeline ------------------------------------------------------------------------
+static int ensure_buffers(hb_ctx *ctx, uint64_t in_words, uint64_t out_words)
+{
+    if (in_words > ctx->in_buf_words) {
+        cudaFree(ctx->d_in_buf);
+        ctx->d_in_buf = nullptr;
+        ctx->in_buf_words = 0;
+        HB_CUDA(ctx, cudaMalloc(&ctx->d_in_buf, (in_words + 8) * sizeof(uint32_t)));
+        ctx->in_buf_words = in_words;
+    }
+    if (out_words > ctx->out_buf_words) {
+        cudaFree(ctx->d_out_buf);
+        ctx->d_out_buf = nullptr;
+        ctx->out_buf_words = 0;
+        HB_CUDA(ctx, cudaMalloc(&ctx->d_out_buf, (out_words + 8) * sizeof(uint32_t)));
+        ctx->out_buf_words = out_words;
+    }
+    return HB_OK;
+}
+
+int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint32_t *h_out,
+                       uint64_t out_capacity_words, const uint32_t codewords[256],
+                       const uint32_t codewordlens[256], uint64_t *out_bytes, uint64_t *total_bits)
+{
+    if (!ctx || !h_out || !codewords || !codewordlens || (!h_in && n_words)) return HB_ERR_ARG;
+    if (n_words > ctx->max_words) return HB_ERR_CAPACITY;
+    if (out_capacity_words == 0) return HB_ERR_CAPACITY;
+    DeviceGuard g(ctx->device);
+
+    uint32_t max_len = 0;
+    for (int s = 0; s < 256; s++) {
+        if (codewordlens[s] > HB_MAX_CODE_LEN) return HB_ERR_CODELEN;
+        if (codewordlens[s] > max_len) max_len = codewordlens[s];
+    }
+    // device output: never more than the caller can take, never more than the worst case
+    uint64_t worst = (n_words * 4 * (uint64_t)max_len) / 32 + 2;
+    uint64_t dev_out_words = worst < out_capacity_words ? worst : out_capacity_words;
+    int rc = ensure_buffers(ctx, n_words, dev_out_words);
+    if (rc != HB_OK) return rc;
+
+    cudaStream_t st = ctx->s_main;
+    if (ctx->pending) {                        // un-fetched async encodes: drain them first
+        HB_CUDA(ctx, cudaDeviceSynchronize());
+        ctx->pending = false;
+    }
+    if ((rc = set_codebook(ctx, codewords, codewordlens, st)) != HB_OK) return rc;
+    ctx->h_result->overflow = 0;
+    ctx->h_result->bits_end = 0;
+
+    uint64_t bits = 0;
+    if (n_words == 0) {
+        h_out[0] = 0;                          // cpuencode.cpp:17
+    } else {
+        if ((rc = next_epoch(ctx, st)) != HB_OK) return rc;
+        // Chunked: the H2D copy of chunk k+1 overlaps the encode of chunk k.  All chunks belong to ONE
+        // job (one descriptor array, one output stream); a later launch looks back into the
+        // descriptors and symbols of the earlier ones.
+        const uint64_t total_tiles = tiles_of(n_words);
+        uint64_t chunk_tiles = (32ull << 20) / hb::kTileBytes;           // 32 MiB of input per chunk
+        static const char *env = getenv("HB_CHUNK_MIB");
+        if (env && atoi(env) > 0) chunk_tiles = ((uint64_t)atoi(env) << 20) / hb::kTileBytes;
+        for (uint64_t t0 = 0; t0 < total_tiles; t0 += chunk_tiles) {
+            const uint64_t t1 = (t0 + chunk_tiles < total_tiles) ? t0 + chunk_tiles : total_tiles;
+            const uint64_t w0 = t0 * hb::kTileWords;
+            const uint64_t w1 = (t1 * hb::kTileWords < n_words) ? t1 * hb::kTileWords : n_words;
+            HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_buf + w0, h_in + w0, (w1 - w0) * sizeof(uint32_t),
+                                         cudaMemcpyHostToDevice, st));
+            rc = launch_tiles(ctx, ctx->d_in_buf, n_words, t0, t1, ctx->d_out_buf, dev_out_words, 0, st);
+            if (rc != HB_OK) return rc;
+        }
+        HB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->h_result->overflow) return HB_ERR_CAPACITY;
+        bits = ctx->h_result->bits_end;
+        // floor(bits/32)+1 words, like the reference (the word after an aligned end is zero)
+        uint64_t copy_words = bits / 32 + 1;
+        if (copy_words > out_capacity_words) copy_words = out_capacity_words;
+        if (copy_words < (bits + 31) / 32) return HB_ERR_CAPACITY;
+        HB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_out_buf, copy_words * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, st));
+        HB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (total_bits) *total_bits = bits;
+    if (out_bytes) *out_bytes = (bits + 7) / 8;
+    return HB_OK;
+}
+
+static hb_ctx *g_default_ctx = nullptr;
+static std::mutex g_default_mutex;
+
+int hb_vlc_encode(unsigned int *indata, unsigned int num_elements, unsigned int *outdata,
+                  unsigned int *outsize, unsigned int *codewords, unsigned int *codewordlens)
+{
+    if (!outdata || !outsize || !codewords || !codewordlens) return HB_ERR_ARG;
+    std::lock_guard<std::mutex> lock(g_default_mutex);
+    if (!g_default_ctx || g_default_ctx->max_words < num_elements) {
+        const char *dev = getenv("HB_DEVICE");
+        hb_ctx *fresh = nullptr;
+        uint64_t want = num_elements > (1u << 20) ? num_elements : (1u << 20);
+        int rc = hb_init(&fresh, dev ? atoi(dev) : 0, want);
+        if (rc != HB_OK) return rc;
+        hb_free(g_default_ctx);
+        g_default_ctx = fresh;
+    }
+    // The reference signature carries no output capacity: outdata must hold floor(bits/32)+1 words
+    // (cpuencode.cpp:39).  Use the codebook's worst case as the bound.
+    uint32_t max_len = 0;
+    for (int s = 0; s < 256; s++)
+        if (codewordlens[s] > max_len) max_len = codewordlens[s];
+    const uint64_t cap = ((uint64_t)num_elements * 4 * max_len) / 32 + 2;
+    uint64_t bytes = 0;
+    const int rc = hb_vlc_encode_host(g_default_ctx, indata, num_elements, outdata, cap, codewords,
+                                      codewordlens, &bytes, nullptr);
+    if (rc == HB_OK) *outsize = (unsigned int)bytes;    // cpuencode.cpp:45 (uint32 bytes)
+    return rc;
+}
+
+int hb_host_alloc(void **p, uint64_t bytes)
+{
+    if (!p) return HB_ERR_ARG;
+    const cudaError_t e = cudaMallocHost(p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *p = nullptr;
+        return HB_ERR_NOMEM;
+    }
+    return HB_OK;
+}
+
+void hb_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int hb_stitch_seam(hb_ctx *ctx, uint32_t *d_dst, const uint32_t *d_src, uint64_t n_words, void *stream)
+{
+    if (!ctx || (!d_dst && n_words) || (!d_src && n_words)) return HB_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    HB_CUDA(ctx, hb::launch_or_words(d_dst, d_src, n_words, (cudaStream_t)stream));
+    if (n_words) ctx->launches++;
+    return HB_OK;
+}
+
+int hb_synth_fill(hb_ctx *ctx, uint8_t *d_out, uint64_t first, uint64_t n, uint64_t seed, int mode,
+                  int nbits, const uint32_t *thr, int K, const uint8_t *symmap, void *stream)
+{
+    if (!ctx || (!d_out && n) || !thr || K < 1 || K > 256) return HB_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    // thr/symmap are tiny pageable host arrays: the copies below are synchronous w.r.t. the host
+    HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_thr, thr, (size_t)K * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (symmap)
+        HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_symmap, symmap, (size_t)K, cudaMemcpyHostToDevice, st));
+    HB_CUDA(ctx, hb::launch_synth(d_out, first, n, seed, mode, nbits, ctx->d_thr, K,
+                                  symmap ? ctx->d_symmap : nullptr, st));
+    if (n) ctx->launches++;
+    return HB_OK;
+}
+
+uint64_t hb_launch_count(const hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+const char *hb_encode_variant(const uint32_t codewordlens[256])
+{
+    uint32_t max_len = 0;
+    if (!codewordlens) return "?";
+    for (int s = 0; s < 256; s++)
+        if (codewordlens[s] > max_len) max_len = codewordlens[s];
+    if (max_len > HB_MAX_CODE_LEN) return "rejected";
+    return hb::variant_name(hb::pick_variant((int)max_len));
+}
+
+const char *hb_strerror(int status)
+{
+    switch (status) {
+    case HB_OK: return "ok";
+    case HB_ERR_ARG: return "bad argument (NULL, size, or alignment)";
+    case HB_ERR_CAPACITY: return "output or context capacity too small";
+    case HB_ERR_CODELEN: return "codeword length > 31";
+    case HB_ERR_CODEWORD: return "codeword has bits above its length";
+    case HB_ERR_CUDA: return "CUDA error (see hb_last_cuda_error)";
+    case HB_ERR_NOMEM: return "out of memory";
+    case HB_ERR_STATE: return "call sequence error";
+    default: return "unknown status";
+    }
+}
+
+int hb_last_cuda_error(const hb_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
+
+const char *hb_version(void) { return "huffman-b200 0.1 (sm_100a)"; }
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+/*
+ * hb_kernels.cuh -- internal interface between the C-ABI layer (hb_api.cu) and the sm_100a kernels.
+ */
+#ifndef HB_KERNELS_CUH_
+#define HB_KERNELS_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+
+// ---- tile geometry of the single-pass encoder -----------------------------------------------
+constexpr int kEncThreads = 256;                       // threads per CTA
+constexpr int kSymPerThread = 32;                      // symbols (bytes) per thread per tile
+constexpr int kTileBytes = kEncThreads * kSymPerThread;  // 8192 symbols per tile
+constexpr int kTileWords = kTileBytes / 4;             // 2048 input words per tile
+
+// ---- decoupled look-back descriptor: [63:50] epoch | [49:48] status | [47:0] bits ---------------
+constexpr int kDescValueBits = 48;
+constexpr uint64_t kDescValueMask = (1ULL << kDescValueBits) - 1;
+constexpr uint64_t kStatusAggregate = 1;               // value = bits of this tile only
+constexpr uint64_t kStatusPrefix = 2;                  // value = bits up to and including this tile
+constexpr uint32_t kEpochMask = 0x3FFF;
+
+// Written by the kernel into mapped pinned host memory (zero-copy), read by the host after sync.
+struct EncResult {
+    unsigned long long bits_end;      // global bit position after the last tile of the launch
+    unsigned long long overflow;      // != 0: the output did not fit out_cap_words
+};
+
+struct EncParams {
+    const uint32_t *in;               // base of the job's symbol buffer (32-byte aligned)
+    unsigned long long n_words;       // words in the whole job
+    unsigned long long n_tiles;       // tiles in the whole job
+    unsigned long long first_tile;    // this launch encodes tiles [first_tile, end_tile)
+    unsigned long long end_tile;
+    uint32_t *out;
+    unsigned long long out_cap_words;
+    unsigned long long start_bit;     // global bit position of the job's first bit
+    unsigned long long *desc;         // one descriptor per tile of the job
+    unsigned long long *ticket;       // monotonically increasing work counter (never reset)
+    unsigned long long ticket_base;   // counter value at the start of this launch
+    uint32_t epoch;
+    const uint32_t *table;            // packed: uint32[256]; wide: uint2[256] as uint32[512]
+    EncResult *result;
+};
+
+// Encode kernel variants.  "packed": table entry = (cw << (32-len)) | len, needs len <= 24;
+// "wide": entry = {cw << (32-len), len}, len <= 31.  G = symbols appended between two flushes of
+// the 64-bit accumulator; needs G * max_len <= 32.
+enum EncVariant { kPackedG4 = 0, kPackedG3, kPackedG2, kPackedG1, kWideG1, kNumVariants };
+
+const char *variant_name(EncVariant v);
+EncVariant pick_variant(int max_len);
+size_t encode_smem_bytes(EncVariant v);
+cudaError_t encode_configure();                        // opt-in smem attributes, once per process
+cudaError_t launch_encode(EncVariant v, const EncParams &p, int grid, cudaStream_t stream);
+int encode_max_ctas_per_sm(EncVariant v);
+
+cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
+                             unsigned long long *d_hist, int sm_count, cudaStream_t stream);
+cudaError_t launch_or_words(uint32_t *d_dst, const uint32_t *d_src, unsigned long long n_words,
+                            cudaStream_t stream);
+cudaError_t launch_synth(uint8_t *d_out, unsigned long long first, unsigned long long n,
+                         unsigned long long seed, int mode, int nbits, const uint32_t *d_thr, int K,
+                         const uint8_t *d_symmap, cudaStream_t stream);
+
+}  // namespace hb
+#endif

@@ -1,0 +1,167 @@
+/*
+ * hb_misc.cu -- byte histogram, seam OR and the synthetic-input generator for sm_100a.
+ *
+ * Histogram: replaces histo_kernel (hist.cu:34-52: one byte per load, one shared atomicAdd per
+ * byte into a single 256-bin array, 2*SMs blocks) and runHisto's 32 windowed launches
+ * (hist.cu:98-108, which also sample the wrong bytes -- SURVEY.md section 8 a-2).  Here: one
+ * launch over the whole device-resident buffer, 128-bit loads, bins privatised per warp in shared
+ * memory, bytes of a word that are equal are merged into one atomic (adjacent-equal runs are the
+ * common case on skewed data), 64-bit global bins.
+ */
+#include "hb_kernels.cuh"
+
+namespace hb {
+namespace {
+
+constexpr int kHistThreads = 512;
+constexpr int kHistWarps = kHistThreads / 32;
+
+__device__ __forceinline__ void count_word(uint32_t *bins, uint32_t w)
+{
+    const uint32_t b0 = w & 0xFFu, b1 = (w >> 8) & 0xFFu, b2 = (w >> 16) & 0xFFu, b3 = w >> 24;
+    // merge equal neighbours: (b0,b1) and (b2,b3), then the two pairs
+    if (b0 == b1 && b2 == b3) {
+        if (b0 == b2) {
+            atomicAdd(&bins[b0], 4u);
+        } else {
+            atomicAdd(&bins[b0], 2u);
+            atomicAdd(&bins[b2], 2u);
+        }
+    } else {
+        atomicAdd(&bins[b0], 1u);
+        atomicAdd(&bins[b1], 1u);
+        atomicAdd(&bins[b2], 1u);
+        atomicAdd(&bins[b3], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(kHistThreads) hist_kernel(const uint32_t *__restrict__ in,
+                                                            unsigned long long n_words,
+                                                            unsigned long long *__restrict__ hist)
+{
+    __shared__ uint32_t bins[kHistWarps][256];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < kHistWarps * 256; i += kHistThreads) (&bins[0][0])[i] = 0u;
+    __syncthreads();
+
+    uint32_t *mine = bins[tid >> 5];
+    const unsigned long long gtid = (unsigned long long)blockIdx.x * kHistThreads + tid;
+    const unsigned long long stride = (unsigned long long)gridDim.x * kHistThreads;
+
+    // head words up to the first 16-byte boundary, then uint4 body, then tail words
+    const unsigned long long mis = ((16u - ((unsigned long long)(uintptr_t)in & 15u)) & 15u) / 4u;
+    const unsigned long long head = mis < n_words ? mis : n_words;
+    const unsigned long long n_vec = (n_words - head) / 4;
+    const uint4 *vec = reinterpret_cast<const uint4 *>(in + head);
+    for (unsigned long long i = gtid; i < n_vec; i += stride) {
+        const uint4 v = __ldg(vec + i);
+        count_word(mine, v.x);
+        count_word(mine, v.y);
+        count_word(mine, v.z);
+        count_word(mine, v.w);
+    }
+    const unsigned long long rest0 = head + n_vec * 4;
+    if (gtid < head) count_word(mine, in[gtid]);
+    if (gtid < n_words - rest0) count_word(mine, in[rest0 + gtid]);
+    __syncthreads();
+
+    for (uint32_t b = tid; b < 256; b += kHistThreads) {
+        unsigned long long sum = 0;
+#pragma unroll
+        for (int w = 0; w < kHistWarps; w++) sum += bins[w][b];
+        if (sum) atomicAdd(&hist[b], sum);
+    }
+}
+
+__global__ void or_words_kernel(uint32_t *dst, const uint32_t *src, unsigned long long n)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] |= src[i];
+}
+
+// ---- synthetic inputs (same arithmetic as oracle.c orc_synth_fill) ----------
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ uint32_t perm_bits(unsigned long long i, unsigned long long seed, int nbits)
+{
+    const unsigned long long mask = (nbits >= 64) ? ~0ULL : ((1ULL << nbits) - 1ULL);
+    unsigned long long x = (i + seed) & mask;
+    x = (x * 0x9E3779B97F4A7C15ULL) & mask;
+    x ^= x >> (nbits / 2 + 1);
+    x = (x * 0xBF58476D1CE4E5B9ULL) & mask;
+    x ^= x >> (nbits / 2);
+    x = (x * 0x94D049BB133111EBULL) & mask;
+    x ^= x >> (nbits / 2 + 2);
+    return (uint32_t)x;
+}
+
+__global__ void __launch_bounds__(256) synth_kernel(uint8_t *out, unsigned long long first,
+                                                    unsigned long long n, unsigned long long seed,
+                                                    int mode, int nbits, const uint32_t *thr, int K,
+                                                    const uint8_t *symmap)
+{
+    __shared__ uint32_t s_thr[256];
+    __shared__ uint8_t s_map[256];
+    for (int k = threadIdx.x; k < 256; k += 256) {
+        s_thr[k] = (k < K) ? thr[k] : 0xFFFFFFFFu;
+        s_map[k] = symmap ? symmap[k] : (uint8_t)k;
+    }
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += stride) {
+        const unsigned long long i = first + j;
+        const uint32_t u = (mode == 0)
+                               ? (uint32_t)(mix64(seed + (i + 1ULL) * 0x9E3779B97F4A7C15ULL) >> 32)
+                               : perm_bits(i, seed, nbits);
+        int lo = 0, hi = K - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (u < s_thr[mid]) hi = mid; else lo = mid + 1;
+        }
+        out[j] = s_map[lo];
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
+                             unsigned long long *d_hist, int sm_count, cudaStream_t stream)
+{
+    if (n_words == 0) return cudaSuccess;
+    unsigned long long want = (n_words / 4 + kHistThreads - 1) / kHistThreads;
+    if (want < 1) want = 1;
+    const unsigned long long cap = (unsigned long long)sm_count * 4;
+    const int grid = (int)(want < cap ? want : cap);
+    hist_kernel<<<grid, kHistThreads, 0, stream>>>(d_in, n_words, d_hist);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_or_words(uint32_t *d_dst, const uint32_t *d_src, unsigned long long n_words,
+                            cudaStream_t stream)
+{
+    if (n_words == 0) return cudaSuccess;
+    const int threads = 256;
+    const unsigned long long grid = (n_words + threads - 1) / threads;
+    or_words_kernel<<<(unsigned)grid, threads, 0, stream>>>(d_dst, d_src, n_words);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_synth(uint8_t *d_out, unsigned long long first, unsigned long long n,
+                         unsigned long long seed, int mode, int nbits, const uint32_t *d_thr, int K,
+                         const uint8_t *d_symmap, cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    unsigned long long grid = (n + 255) / 256;
+    if (grid > 148ULL * 32) grid = 148ULL * 32;
+    synth_kernel<<<(unsigned)grid, 256, 0, stream>>>(d_out, first, n, seed, mode, nbits, d_thr, K,
+                                                     d_symmap);
+    return cudaGetLastError();
+}
+
+}  // namespace hb

@@ -1,0 +1,146 @@
+/*
+ * huffman_b200.h -- C ABI of libhuffb200.so: the B200-native (sm_100a) Huffman variable-length
+ * ENCODE hot path, a drop-in for the reference's histogram -> codebook -> encode -> scan -> pack
+ * sequence (vlnguyen92/Huffman-GPU, main_test_cu.cu:85-170).
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types (a stream is passed as the opaque
+ * cudaStream_t value, `void *`; NULL = the legacy default stream).  Every function returns an
+ * hb_status (0 = ok, negative = error); nothing ever calls exit() (the reference does:
+ * cutil.h:781-787, hist.cu:19-27).
+ *
+ * Conventions shared with the reference (cpuencode.h:4-7, cpuencode.cpp:12-46):
+ *   - input  = symbols packed 4 per little-endian uint32, consumed MOST SIGNIFICANT BYTE FIRST;
+ *   - tables = codewords[256] (right-aligned values) and codewordlens[256] (bits), host memory;
+ *   - output = one contiguous bitstream in uint32 words, stream bit j = bit 31-(j%32) of word j/32,
+ *              unused low bits of the last word zero, bit-identical to cpu_vlc_encode.
+ * Parity domain: codeword lengths 0..31 and codewords[s] < 2^codewordlens[s] (cpuencode.cpp:34
+ * is undefined for length 32 and does not mask straddling codewords).
+ * Anything else is rejected with HB_ERR_CODELEN / HB_ERR_CODEWORD.
+ *
+ * There is NO CPU fallback: every data-path entry point fails with HB_ERR_CUDA when no sm_100
+ * device / kernel image is available.
+ */
+#ifndef HUFFMAN_B200_H_
+#define HUFFMAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_NUM_SYMBOLS 256          /* parameters.h:25 NUM_SYMBOLS */
+#define HB_MAX_CODE_LEN 31          /* parity domain of cpu_vlc_encode */
+
+typedef enum {
+    HB_OK = 0,
+    HB_ERR_ARG = -1,        /* NULL pointer, bad size, misaligned device pointer */
+    HB_ERR_CAPACITY = -2,   /* output (or context scratch) too small */
+    HB_ERR_CODELEN = -3,    /* a used codeword length is > 31 (or a histogram needs > 31 bits) */
+    HB_ERR_CODEWORD = -4,   /* codewords[s] has bits set at or above codewordlens[s] */
+    HB_ERR_CUDA = -5,       /* CUDA runtime error; see hb_last_cuda_error() */
+    HB_ERR_NOMEM = -6,
+    HB_ERR_STATE = -7       /* call sequence error (e.g. hb_encode_result without hb_encode_async) */
+} hb_status;
+
+typedef struct hb_ctx hb_ctx;
+
+/* ---- lifecycle (replaces InitCUDA, cuda_helpers.h:11-38, and the cudaMalloc block of
+ *      runVLCTest, main_test_cu.cu:93-110; scan.cu:67-112 preallocBlockSums/deallocBlockSums).
+ * The context owns only scratch: tile descriptors for inputs up to `max_words` uint32 words, the
+ * device copy of the codebook, a pinned result block.  One context per (host thread, device);
+ * calls on a context are ordered on the stream they are given.  No hidden globals. */
+int hb_init(hb_ctx **ctx, int device, uint64_t max_words);
+void hb_free(hb_ctx *ctx);
+
+/* ---- byte histogram of a device buffer (replaces runHisto/histo_kernel, hist.cu:34-125, minus
+ *      the file read and minus runHisto's window bug: this counts ALL 4*n_words bytes).
+ * d_in: device pointer, 4-byte aligned.  hist: HOST array, 64-bit counts.  Synchronises `stream`. */
+int hb_histogram(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t hist[256],
+                 void *stream);
+/* Same, but ADDS into a DEVICE array of 256 uint64 and does not synchronise (multi-GPU path: the
+ * caller all-reduces d_hist with NCCL before building the codebook). */
+int hb_histogram_device(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t *d_hist,
+                        void *stream);
+
+/* ---- host-side codebook (replaces BuildTree + GenerateCodes, huffTree.h:55-94, and the table
+ *      flatten of loadData, load_data.h:40-47).  Pure function, no device work.  Tie-breaking is
+ *      identical to std::priority_queue<INode*, vector<INode*>, NodeCmp>; weights are 64-bit.
+ * Returns the maximum code length (>= 0) or HB_ERR_CODELEN if a code would exceed 31 bits. */
+int hb_build_codebook(const uint64_t hist[256], uint32_t codewords[256],
+                      uint32_t codewordlens[256]);
+
+/* sum_s hist[s] * codewordlens[s]: the exact output size in bits, known before encoding
+ * (used to derive per-shard start bits without an extra pass). */
+uint64_t hb_bits_from_hist(const uint64_t hist[256], const uint32_t codewordlens[256]);
+
+/* ---- single-pass encode (replaces vlc_encode_kernel_sm64huff + prescanArray + cudaMemset +
+ *      pack2, main_test_cu.cu:142-166, and is bit-exact with cpu_vlc_encode, cpuencode.cpp:12-46).
+ * d_in:   device, 32-byte aligned, n_words uint32 (4 symbols each).
+ * d_out:  device, 4-byte aligned, capacity in words.  No pre-zeroing needed.  Words
+ *         [start_bit/32, ceil((start_bit+bits)/32)) are written; like the reference
+ *         (cpuencode.cpp:39) one extra zero word is written after a word-aligned end when it
+ *         fits.  The `start_bit % 32` leading bits of the first word are written as ZERO (a shard
+ *         seam is OR-ed by the caller, see hb_stitch_seam).
+ * start_bit: global bit position of this stream's first bit (0 for a single-GPU encode).
+ * total_bits: HOST pointer; receives the number of bits produced (excluding start_bit).
+ * hb_encode synchronises `stream`; hb_encode_async does not (fetch with hb_encode_result). */
+int hb_encode(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const uint32_t codewords[256],
+              const uint32_t codewordlens[256], uint32_t *d_out, uint64_t out_capacity_words,
+              uint64_t start_bit, uint64_t *total_bits, void *stream);
+int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words,
+                    const uint32_t codewords[256], const uint32_t codewordlens[256],
+                    uint32_t *d_out, uint64_t out_capacity_words, uint64_t start_bit,
+                    void *stream);
+int hb_encode_result(hb_ctx *ctx, uint64_t *total_bits, void *stream);
+
+/* ---- host-buffer entry points (the call a reference user makes today) ------------------------
+ * hb_vlc_encode has EXACTLY the signature and semantics of the reference's
+ *   extern "C" void cpu_vlc_encode(unsigned int *indata, unsigned int num_elements,
+ *        unsigned int *outdata, unsigned int *outsize, unsigned int *codewords,
+ *        unsigned int *codewordlens)                                   (cpuencode.h:4-7)
+ * with HOST pointers: outsize is in BYTES = ceil(bits/8) (cpuencode.cpp:44-45) and outdata needs
+ * floor(bits/32)+1 words.  It runs H2D -> GPU encode -> D2H on a lazily created per-process
+ * context (device = $HB_DEVICE or 0) and returns an hb_status instead of void.
+ * hb_vlc_encode_host is the same with 64-bit sizes, an explicit context and capacity, and chunked
+ * copy/encode overlap; buffers from hb_host_alloc (pinned) are copied by DMA directly. */
+int hb_vlc_encode(unsigned int *indata, unsigned int num_elements, unsigned int *outdata,
+                  unsigned int *outsize, unsigned int *codewords, unsigned int *codewordlens);
+int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint32_t *h_out,
+                       uint64_t out_capacity_words, const uint32_t codewords[256],
+                       const uint32_t codewordlens[256], uint64_t *out_bytes,
+                       uint64_t *total_bits);
+int hb_host_alloc(void **p, uint64_t bytes);      /* pinned host memory */
+void hb_host_free(void *p);
+
+/* ---- multi-GPU helpers (no reference equivalent) ------------------------
+ * hb_shard_offsets: exclusive prefix of per-shard bit totals -> start_bit of every shard. */
+int hb_shard_offsets(const uint64_t *shard_bits, int n_shards, uint64_t *start_bits,
+                     uint64_t *total_bits);
+/* OR `n_words` words of d_src into d_dst (both device, same GPU): merges the seam word(s) that two
+ * neighbouring shards both own after a peer-to-peer gather. */
+int hb_stitch_seam(hb_ctx *ctx, uint32_t *d_dst, const uint32_t *d_src, uint64_t n_words,
+                   void *stream);
+
+/* ---- tooling -----------------------------------------------------------------------------------
+ * Deterministic synthetic input generator on the device (the reference's
+ * testdatagen.h:62-67 cannot control entropy).  Byte i of the stream, i in [first, first+n):
+ *   mode 0: u = splitmix64(seed + (i+1)*0x9E3779B97F4A7C15) >> 32
+ *   mode 1: u = perm_nbits(i, seed), a bijection on [0, 2^nbits)
+ *   sym = first k < K-1 with u < thr[k], else K-1;  byte = symmap ? symmap[sym] : sym.
+ * thr / symmap are HOST arrays (K <= 256). */
+int hb_synth_fill(hb_ctx *ctx, uint8_t *d_out, uint64_t first, uint64_t n, uint64_t seed, int mode,
+                  int nbits, const uint32_t *thr, int K, const uint8_t *symmap, void *stream);
+
+/* Kernel launches issued through this context so far (bench.py's gpu_launches counter). */
+uint64_t hb_launch_count(const hb_ctx *ctx);
+/* Name of the encode kernel variant chosen for a codebook ("packed_g2", "wide_g1", ...). */
+const char *hb_encode_variant(const uint32_t codewordlens[256]);
+const char *hb_strerror(int status);
+int hb_last_cuda_error(const hb_ctx *ctx);        /* cudaError_t of the last HB_ERR_CUDA */
+const char *hb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUFFMAN_B200_H_ */
