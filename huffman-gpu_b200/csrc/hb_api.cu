@@ -36,7 +36,8 @@ struct hb_ctx {
     uint32_t cw_cache[256];
     uint32_t len_cache[256];
     bool table_valid = false;
-    hb::EncVariant variant = hb::kPackedG1;
+    int forced = 0;                           // $HB_FORCE_GROUP the cached table was packed under
+    hb::EncVariant variant = {1, false, false};
 
     hb::EncResult *h_result = nullptr;        // mapped pinned; the kernel writes it directly
     uint64_t pending_start_bit = 0;
@@ -94,22 +95,41 @@ struct DeviceGuard {
     }
 };
 
+// The kernel variant for a codebook; $HB_FORCE_GROUP overrides the group size (tuning aid only).
+int forced_group()
+{
+    const char *env = getenv("HB_FORCE_GROUP");
+    return env ? atoi(env) : 0;
+}
+
+hb::EncVariant choose_variant(const uint32_t len[256])
+{
+    hb::EncVariant v = hb::pick_variant(len);
+    const int g = forced_group();
+    if (g == 1 || g == 2 || g == 4 || (!v.wide && (g == 3 || g == 6 || g == 8))) {
+        uint32_t max_len = 0;
+        for (int s = 0; s < 256; s++)
+            if (len[s] > max_len) max_len = len[s];
+        v.group = g;
+        v.check = g > 1 && (v.wide || (uint32_t)g * max_len > 31u);
+    }
+    return v;
+}
+
 // Validate the caller's tables against the parity domain and pack them for the kernel.
 int pack_tables(const uint32_t cw[256], const uint32_t len[256], uint32_t packed[512],
                 hb::EncVariant *variant)
 {
-    uint32_t max_len = 0;
     for (int s = 0; s < 256; s++) {
         if (len[s] > HB_MAX_CODE_LEN) return HB_ERR_CODELEN;
         if (len[s] < 32 && (cw[s] >> len[s]) != 0) return HB_ERR_CODEWORD;
-        if (len[s] > max_len) max_len = len[s];
     }
-    const hb::EncVariant v = hb::pick_variant((int)max_len);
+    const hb::EncVariant v = choose_variant(len);
     memset(packed, 0, 512 * sizeof(uint32_t));
     for (int s = 0; s < 256; s++) {
         const uint32_t l = len[s];
         const uint32_t left = l ? (cw[s] << (32u - l)) : 0u;
-        if (v == hb::kWideG1) {
+        if (v.wide) {
             packed[2 * s] = left;
             packed[2 * s + 1] = l;
         } else {
@@ -122,7 +142,8 @@ int pack_tables(const uint32_t cw[256], const uint32_t len[256], uint32_t packed
 
 int set_codebook(hb_ctx *ctx, const uint32_t cw[256], const uint32_t len[256], cudaStream_t stream)
 {
-    if (ctx->table_valid && memcmp(cw, ctx->cw_cache, sizeof(ctx->cw_cache)) == 0 &&
+    const int forced = forced_group();
+    if (ctx->table_valid && forced == ctx->forced && memcmp(cw, ctx->cw_cache, sizeof(ctx->cw_cache)) == 0 &&
         memcmp(len, ctx->len_cache, sizeof(ctx->len_cache)) == 0)
         return HB_OK;
     uint32_t packed[512];
@@ -138,6 +159,7 @@ int set_codebook(hb_ctx *ctx, const uint32_t cw[256], const uint32_t len[256], c
     memcpy(ctx->cw_cache, cw, sizeof(ctx->cw_cache));
     memcpy(ctx->len_cache, len, sizeof(ctx->len_cache));
     ctx->variant = v;
+    ctx->forced = forced;
     ctx->table_valid = true;
     return HB_OK;
 }
@@ -165,12 +187,9 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
     p.table = ctx->d_table;
     p.result = ctx->h_result;
 
+    // one persistent CTA per SM (its shared memory holds the 64 KiB table and the staging rings)
     const uint64_t tiles = end_tile - first_tile;
-    int per_sm = hb::encode_max_ctas_per_sm(ctx->variant);
-    if (per_sm < 1) return cuda_fail(ctx, cudaErrorInvalidConfiguration);
-    static const char *env = getenv("HB_CTAS_PER_SM");
-    if (env && atoi(env) > 0 && atoi(env) < per_sm) per_sm = atoi(env);
-    uint64_t grid = (uint64_t)ctx->sm_count * (uint64_t)per_sm;
+    uint64_t grid = (uint64_t)ctx->sm_count;
     if (grid > tiles) grid = tiles;
     HB_CUDA(ctx, hb::launch_encode(ctx->variant, p, (int)grid, stream));
     ctx->ticket_base += tiles + grid;      // every CTA draws exactly one ticket past the end
@@ -338,10 +357,11 @@ int hb_encode_result(hb_ctx *ctx, uint64_t *total_bits, void *stream)
     DeviceGuard g(ctx->device);
     HB_CUDA(ctx, cudaStreamSynchronize((cudaStream_t)stream));
     ctx->pending = false;
-    const bool overflow = ctx->h_result->overflow != 0;
+    const unsigned long long overflow = ctx->h_result->overflow;
     ctx->h_result->overflow = 0;
     if (total_bits)
         *total_bits = ctx->pending_empty ? 0 : ctx->h_result->bits_end - ctx->pending_start_bit;
+    if (overflow == 2ULL) return HB_ERR_STATE;      // the kernel refused its shared-memory layout
     return overflow ? HB_ERR_CAPACITY : HB_OK;
 }
 
@@ -426,6 +446,7 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
             if (rc != HB_OK) return rc;
         }
         HB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->h_result->overflow == 2ULL) return HB_ERR_STATE;
         if (ctx->h_result->overflow) return HB_ERR_CAPACITY;
         bits = ctx->h_result->bits_end;
         // floor(bits/32)+1 words, like the reference (the word after an aligned end is zero)
@@ -517,12 +538,10 @@ uint64_t hb_launch_count(const hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 const char *hb_encode_variant(const uint32_t codewordlens[256])
 {
-    uint32_t max_len = 0;
     if (!codewordlens) return "?";
     for (int s = 0; s < 256; s++)
-        if (codewordlens[s] > max_len) max_len = codewordlens[s];
-    if (max_len > HB_MAX_CODE_LEN) return "rejected";
-    return hb::variant_name(hb::pick_variant((int)max_len));
+        if (codewordlens[s] > HB_MAX_CODE_LEN) return "rejected";
+    return hb::variant_name(choose_variant(codewordlens));
 }
 
 const char *hb_strerror(int status)

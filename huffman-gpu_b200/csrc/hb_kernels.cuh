@@ -9,11 +9,15 @@
 
 namespace hb {
 
-// ---- tile geometry of the single-pass encoder -----------------------------------------------
-constexpr int kEncThreads = 256;                       // threads per CTA
-constexpr int kSymPerThread = 32;                      // symbols (bytes) per thread per tile
-constexpr int kTileBytes = kEncThreads * kSymPerThread;  // 8192 symbols per tile
-constexpr int kTileWords = kTileBytes / 4;             // 2048 input words per tile
+// ---- geometry of the single-pass encoder ---------------------------------------------------------
+// One persistent CTA per SM: kEncWorkers worker warps + 1 scout warp.  A tile is the CTA's unit of
+// work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
+constexpr int kEncWorkers = 16;
+constexpr int kEncThreads = (kEncWorkers + 1) * 32;
+constexpr int kSymPerThread = 32;                                     // symbols (bytes) per thread per tile
+constexpr int kChunkBytes = 32 * kSymPerThread;                       // one warp: 1 KiB
+constexpr int kTileBytes = kEncWorkers * kChunkBytes;                 // 16 KiB
+constexpr int kTileWords = kTileBytes / 4;
 
 // ---- decoupled look-back descriptor: [63:50] epoch | [49:48] status | [47:0] bits ---------------
 constexpr int kDescValueBits = 48;
@@ -45,17 +49,25 @@ struct EncParams {
     EncResult *result;
 };
 
-// Encode kernel variants.  "packed": table entry = (cw << (32-len)) | len, needs len <= 24;
-// "wide": entry = {cw << (32-len), len}, len <= 31.  G = symbols appended between two flushes of
-// the 64-bit accumulator; needs G * max_len <= 32.
-enum EncVariant { kPackedG4 = 0, kPackedG3, kPackedG2, kPackedG1, kWideG1, kNumVariants };
+// Encode kernel variants.
+//   "packed": table entry = (cw << (32-len)) | len, needs every len <= 24;
+//   "wide":   entry = {cw << (32-len), len}, len <= 31.
+//   G = symbols whose codewords are chained in one 32-bit register before the word-boundary test.
+//   A group must stay below 32 bits; when G * max_len > 31 that is checked at run time (CHECK) and
+//   a warp that meets such a group re-encodes its chunk symbol by symbol.
+struct EncVariant {
+    int group;        // G in {1, 2, 3, 4, 6, 8}
+    bool wide;
+    bool check;
+};
 
-const char *variant_name(EncVariant v);
-EncVariant pick_variant(int max_len);
-size_t encode_smem_bytes(EncVariant v);
+// Picks the variant from the code lengths alone (2^-len is the symbol probability a Huffman code
+// implies): the largest G whose chance of an over-long group is negligible.
+EncVariant pick_variant(const uint32_t codewordlens[256]);
+const char *variant_name(const EncVariant &v);
+size_t encode_smem_bytes(const EncVariant &v);
 cudaError_t encode_configure();                        // opt-in smem attributes, once per process
-cudaError_t launch_encode(EncVariant v, const EncParams &p, int grid, cudaStream_t stream);
-int encode_max_ctas_per_sm(EncVariant v);
+cudaError_t launch_encode(const EncVariant &v, const EncParams &p, int grid, cudaStream_t stream);
 
 cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
                              unsigned long long *d_hist, int sm_count, cudaStream_t stream);

@@ -8,7 +8,7 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TILE = 8192
+TILE = 16384          # hb::kTileBytes: 16 worker warps x 1 KiB chunks
 
 
 @pytest.fixture(scope="module")
@@ -145,7 +145,9 @@ def random_prefix_code(rng, nsym, skew):
     h = np.zeros(256, dtype=np.uint64)
     syms = rng.choice(256, size=nsym, replace=False)
     if skew == "geo":
-        h[syms] = np.maximum(1, (2.0 ** 30 * rng.uniform(0.3, 0.97) ** np.arange(nsym))).astype(np.uint64)
+        # ratio floor keeps the deepest code at <= 31 bits (the parity domain)
+        r = rng.uniform(max(0.3, 2.0 ** (-26.0 / nsym)), 0.97)
+        h[syms] = np.maximum(1, (2.0 ** 30 * r ** np.arange(nsym))).astype(np.uint64)
     elif skew == "flat":
         h[syms] = rng.integers(1, 1000, size=nsym)
     else:                                                        # fibonacci: the deepest trees
@@ -158,7 +160,8 @@ def random_prefix_code(rng, nsym, skew):
 
 @pytest.mark.parametrize("skew,nsym", [("geo", 2), ("geo", 22), ("geo", 64), ("geo", 256), ("flat", 256),
                                        ("flat", 3), ("fib", 17), ("fib", 25), ("fib", 32)])
-@pytest.mark.parametrize("n_bytes", [4, 8188, 8192, 8196, 3 * 8192 + 20, 1_000_000, 5 * 1024 * 1024 + 4])
+@pytest.mark.parametrize("n_bytes", [4, 1020, 1024, 16380, 16384, 16388, 3 * 16384 + 20, 1_000_000,
+                                     5 * 1024 * 1024 + 4])
 def test_random_codebooks(hb, enc, orc, torch_mod, skew, nsym, n_bytes):
     import zlib
     rng = np.random.default_rng(zlib.crc32(repr((skew, nsym, n_bytes)).encode()))
@@ -172,13 +175,34 @@ def test_random_codebooks(hb, enc, orc, torch_mod, skew, nsym, n_bytes):
     check_against_oracle(orc, enc, torch_mod, data, cw, cl)
 
 
-def test_all_variants_exercised(hb):
-    seen = set()
-    for max_len in (1, 8, 9, 10, 11, 16, 17, 24, 25, 31):
+def test_variant_choice(hb, c1):
+    """the kernel variant follows from the code lengths alone (group size G, packed/wide table, run-time check)"""
+    want = {1: "packed_g8", 3: "packed_g8", 5: "packed_g6", 7: "packed_g4", 10: "packed_g3", 15: "packed_g2",
+            16: "packed_g1", 24: "packed_g1", 25: "wide_g1", 31: "wide_g1"}
+    for max_len, name in want.items():
         cl = np.zeros(256, np.uint32)
-        cl[0] = max_len
+        cl[0] = cl[1] = max_len
+        assert hb.encode_variant(cl) == name, max_len
+    assert hb.encode_variant(c1["codewordlens"]) == "packed_g4c"      # skewed: long codes are rare
+
+
+@pytest.mark.parametrize("group", [1, 2, 3, 4, 6, 8])
+def test_every_kernel_variant_vs_oracle(hb, enc, orc, torch_mod, monkeypatch, group):
+    """$HB_FORCE_GROUP pins G; each (G, packed|wide, check|nocheck) kernel must equal cpu_vlc_encode, on data
+    that follows the codebook (fast path) and on data that does not (over-long groups -> symbol-by-symbol path)"""
+    monkeypatch.setenv("HB_FORCE_GROUP", str(group))
+    rng = np.random.default_rng(group)
+    seen = set()
+    for skew, nsym in (("flat", 6), ("geo", 22), ("flat", 256), ("fib", 32)):
+        h = random_prefix_code(rng, nsym, skew)
+        cw, cl, max_len = hb.build_codebook(h)
         seen.add(hb.encode_variant(cl))
-    assert seen == {"packed_g4", "packed_g3", "packed_g2", "packed_g1", "wide_g1"}
+        p = h.astype(np.float64) / float(h.sum())
+        matched = rng.choice(256, size=6 * TILE + 1000, p=p).astype(np.uint8)
+        check_against_oracle(orc, enc, torch_mod, matched, cw, cl)
+        uniform = rng.choice(np.nonzero(h)[0], size=2 * TILE + 36).astype(np.uint8)   # rare symbols everywhere
+        check_against_oracle(orc, enc, torch_mod, uniform, cw, cl)
+    assert len(seen) >= 2, seen
 
 
 @pytest.mark.parametrize("max_len", [1, 5, 8, 10, 13, 16, 20, 24, 27, 31])
@@ -190,7 +214,7 @@ def test_arbitrary_tables_lengths_0_to_31(enc, orc, torch_mod, max_len):
         cl = rng.integers(lo, max_len + 1, size=256).astype(np.uint32)
         cl[rng.integers(0, 256)] = max_len
         cw = np.array([int(rng.integers(0, 1 << int(l))) if l else 0 for l in cl], dtype=np.uint32)
-        n_bytes = [40, 8192 * 3, 200_004][trial]
+        n_bytes = [40, TILE * 3, 200_004][trial]
         data = rng.integers(0, 256, size=n_bytes, dtype=np.uint8)
         check_against_oracle(orc, enc, torch_mod, data, cw, cl)
 
@@ -203,14 +227,14 @@ def test_mostly_zero_length_codes(enc, orc, torch_mod):
     cl[9], cw[9] = 3, 0b101
     cl[200], cw[200] = 31, 0x5EADBEEF & 0x7FFFFFFF
     for density in (0.0, 0.0005, 0.05):
-        data = np.zeros(8192 * 6 + 64, dtype=np.uint8)
+        data = np.zeros(TILE * 6 + 64, dtype=np.uint8)
         hits = rng.random(data.size) < density
         data[hits] = rng.choice([9, 200], size=int(hits.sum()))
         check_against_oracle(orc, enc, torch_mod, data, cw, cl)
 
 
 def test_single_symbol_input(hb, enc, orc, torch_mod):
-    data = np.full(8192 * 2 + 16, 77, dtype=np.uint8)
+    data = np.full(TILE * 2 + 16, 77, dtype=np.uint8)
     h = orc.histogram(data)
     cw, cl, max_len = hb.build_codebook(h)
     assert max_len == 0
@@ -223,7 +247,7 @@ def test_single_symbol_input(hb, enc, orc, torch_mod):
 def test_start_bit_phase(hb, enc, orc, torch_mod, start_bit):
     rng = np.random.default_rng(start_bit)
     w = hb.workloads.get("c2")
-    data = orc.synth_fill(0, 8192 * 5 + 400, w.seed, w.mode, w.nbits, w.thr)
+    data = orc.synth_fill(0, TILE * 5 + 400, w.seed, w.mode, w.nbits, w.thr)
     cw, cl, _ = hb.build_codebook(orc.histogram(data))
     ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
     out, bits = gpu_encode(enc, torch_mod, data, cw, cl, start_bit=start_bit)
@@ -240,13 +264,13 @@ def test_start_bit_phase(hb, enc, orc, torch_mod, start_bit):
 
 
 def test_capacity_error(hb, enc, orc, torch_mod):
-    data = np.random.default_rng(0).integers(0, 256, size=8192 * 4, dtype=np.uint8)
+    data = np.random.default_rng(0).integers(0, 256, size=TILE * 4, dtype=np.uint8)
     cw, cl, _ = hb.build_codebook(orc.histogram(data))
     with pytest.raises(hb.HBError) as e:
         gpu_encode(enc, torch_mod, data, cw, cl, cap_words=100)
     assert e.value.status == hb.capi.HB_ERR_CAPACITY
     check_against_oracle(orc, enc, torch_mod, data, cw, cl)       # the context is still usable
-    big = hb.Encoder(device=0, max_bytes=8192)
+    big = hb.Encoder(device=0, max_bytes=TILE)
     with pytest.raises(hb.HBError) as e:
         gpu_encode(big, torch_mod, data, cw, cl)
     assert e.value.status == hb.capi.HB_ERR_CAPACITY
@@ -266,7 +290,7 @@ def test_repeated_calls_and_two_contexts(hb, enc, orc, torch_mod):
 
 
 def test_non_default_stream(hb, enc, orc, torch_mod):
-    data = np.random.default_rng(5).integers(0, 64, size=8192 * 9 + 12, dtype=np.uint8)
+    data = np.random.default_rng(5).integers(0, 64, size=TILE * 9 + 12, dtype=np.uint8)
     cw, cl, _ = hb.build_codebook(orc.histogram(data))
     s = torch_mod.cuda.Stream()
     with torch_mod.cuda.stream(s):
@@ -288,7 +312,7 @@ def test_vlc_encode_drop_in_signature(hb, orc, ref, c1):
         assert r_size == outsize and np.array_equal(r_out[:nw], out[:nw])
 
 
-@pytest.mark.parametrize("n_bytes,chunk_mib", [(64 << 20, None), ((3 << 20) + 8196, 1), (8192, 1), (4, 1)])
+@pytest.mark.parametrize("n_bytes,chunk_mib", [(64 << 20, None), ((3 << 20) + 16388, 1), (16384, 1), (4, 1)])
 def test_encode_host_chunked(hb, enc, orc, torch_mod, monkeypatch, n_bytes, chunk_mib):
     """H2D -> chunked launches over ONE job -> D2H must equal the single-launch stream"""
     w = hb.workloads.get("c5")
@@ -368,7 +392,7 @@ def test_c4_fibonacci_sample_and_properties(hb, enc, orc, torch_mod):
     hist = big.histogram(d_in)
     assert np.array_equal(hist[:32], hb.workloads.fibonacci_counts())
     cw, cl, max_len = hb.build_codebook(hist)
-    assert max_len == 31 and hb.encode_variant(cl) == "wide_g1"
+    assert max_len == 31 and hb.encode_variant(cl).startswith("wide_")
     g = [c for c in load_golden("codebooks.json") if c.get("name") == "c4_fibonacci"][0]
     assert cw.tolist() == g["codewords"] and cl.tolist() == g["codewordlens"]
     bits_expected = hb.bits_from_hist(hist, cl)

@@ -73,7 +73,7 @@ def test_codebook_c1(hb, c1):
     assert rc == 21
     assert np.array_equal(cw, c1["codewords"]) and np.array_equal(cl, c1["codewordlens"])
     assert hb.bits_from_hist(c1["freqs"], cl) == c1["total_bits"] == 2330672
-    assert hb.encode_variant(cl) == "packed_g1"
+    assert hb.encode_variant(cl) == "packed_g4c"
 
 
 def test_codebook_random_vs_oracle_and_reference(hb, orc, ref):

@@ -77,4 +77,4 @@ def test_shard_bounds():
     b = sharded.shard_bounds(10000, 4)
     assert b[0][0] == 0 and b[-1][1] == 10000
     assert all(b[i][1] == b[i + 1][0] for i in range(3))
-    assert all(lo % 2048 == 0 for lo, hi in b if hi > lo)
+    assert all(lo % 4096 == 0 for lo, hi in b if hi > lo)
