@@ -25,10 +25,11 @@ struct hb_ctx {
     uint64_t max_words = 0;
     uint64_t max_tiles = 0;
 
-    unsigned long long *d_desc = nullptr;     // look-back descriptors, one per tile
+    unsigned long long *d_tree[2] = {nullptr, nullptr};   // look-back Fenwick trees, used by alternate jobs
+    uint64_t tree_dirty[2] = {0, 0};          // entries a job left non-zero (cleared by the next job's kernel)
+    int tree_cur = 0;
     unsigned long long *d_ticket = nullptr;   // monotonically increasing tile ticket
     uint64_t ticket_base = 0;
-    uint32_t epoch = 0;
 
     uint32_t *d_table = nullptr;              // 512 words: packed[256] or wide uint2[256]
     uint32_t *h_table = nullptr;              // pinned staging for the table upload
@@ -57,6 +58,7 @@ struct hb_ctx {
     cudaStream_t s_d2h = nullptr;
     cudaEvent_t ev_chunk = nullptr;
 
+    unsigned long long *d_prof = nullptr;     // $HB_PROFILE: kernel cycle counters, dumped by hb_free
     uint64_t launches = 0;
     int last_cuda = 0;
 };
@@ -180,12 +182,20 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
     p.out = d_out;
     p.out_cap_words = cap_words;
     p.start_bit = start_bit;
-    p.desc = ctx->d_desc;
+    p.tree = ctx->d_tree[ctx->tree_cur];
+    p.tree_zero = ctx->d_tree[ctx->tree_cur ^ 1];
+    p.zero_count = 0;
+    if (first_tile == 0) {
+        // a new job: its kernel clears what the previous job left in the other tree
+        p.zero_count = ctx->tree_dirty[ctx->tree_cur ^ 1];
+        ctx->tree_dirty[ctx->tree_cur ^ 1] = 0;
+        ctx->tree_dirty[ctx->tree_cur] = p.n_tiles;
+    }
     p.ticket = ctx->d_ticket;
     p.ticket_base = ctx->ticket_base;
-    p.epoch = ctx->epoch;
     p.table = ctx->d_table;
     p.result = ctx->h_result;
+    p.prof = ctx->d_prof;
 
     // one persistent CTA per SM (its shared memory holds the 64 KiB table and the staging rings)
     const uint64_t tiles = end_tile - first_tile;
@@ -197,16 +207,8 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
     return HB_OK;
 }
 
-int next_epoch(hb_ctx *ctx, cudaStream_t stream)
-{
-    ctx->epoch = (ctx->epoch + 1) & hb::kEpochMask;
-    if (ctx->epoch == 0) {
-        // tags wrapped: wipe stale descriptors once every 16383 jobs
-        HB_CUDA(ctx, cudaMemsetAsync(ctx->d_desc, 0, ctx->max_tiles * sizeof(unsigned long long), stream));
-        ctx->epoch = 1;
-    }
-    return HB_OK;
-}
+// Every job gets the tree the previous job's kernel cleared.
+void next_job(hb_ctx *ctx) { ctx->tree_cur ^= 1; }
 
 }  // namespace
 
@@ -241,8 +243,10 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     ctx->max_tiles = tiles_of(ctx->max_words) + 1;
 
     bool ok = true;
-    ok = ok && cudaMalloc(&ctx->d_desc, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMemset(ctx->d_desc, 0, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    for (int i = 0; i < 2; i++) {
+        ok = ok && cudaMalloc(&ctx->d_tree[i], ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(ctx->d_tree[i], 0, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    }
     ok = ok && cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_table, 512 * sizeof(uint32_t)) == cudaSuccess;
@@ -255,6 +259,10 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    if (getenv("HB_PROFILE")) {
+        ok = ok && cudaMalloc(&ctx->d_prof, 32 * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(ctx->d_prof, 0, 32 * sizeof(unsigned long long)) == cudaSuccess;
+    }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
         ctx->last_cuda = (int)cudaGetLastError();
@@ -272,7 +280,20 @@ void hb_free(hb_ctx *ctx)
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     (void)cudaDeviceSynchronize();
-    cudaFree(ctx->d_desc);
+    if (ctx->d_prof) {
+        static const char *names[] = {"w0_wait_tile", "w0_wait_prefix", "w0_total", "(unused)", "rs_wait_agg",
+                                      "rs_lookback", "rs_bits_before", "rs_total", "tiles", "lookback_polls",
+                                      "w0_pass1", "w0_emit", "w0_copy"};
+        unsigned long long v[32];
+        if (cudaMemcpy(v, ctx->d_prof, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const double tiles = v[8] ? (double)v[8] : 1.0;
+            for (int i = 0; i < 13; i++)
+                fprintf(stderr, "hb_prof %-16s %14llu  per tile %10.1f\n", names[i], v[i], (double)v[i] / tiles);
+        }
+        cudaFree(ctx->d_prof);
+    }
+    cudaFree(ctx->d_tree[0]);
+    cudaFree(ctx->d_tree[1]);
     cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_table);
     if (ctx->h_table) cudaFreeHost(ctx->h_table);
@@ -341,7 +362,7 @@ int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const u
         ctx->pending_start_bit = start_bit;
         return HB_OK;
     }
-    if ((rc = next_epoch(ctx, st)) != HB_OK) return rc;
+    next_job(ctx);
     rc = launch_tiles(ctx, d_in, n_words, 0, tiles_of(n_words), d_out, out_capacity_words, start_bit, st);
     if (rc != HB_OK) return rc;
     ctx->pending = true;
@@ -428,7 +449,7 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
     if (n_words == 0) {
         h_out[0] = 0;                          // cpuencode.cpp:17
     } else {
-        if ((rc = next_epoch(ctx, st)) != HB_OK) return rc;
+        next_job(ctx);
         // Chunked: the H2D copy of chunk k+1 overlaps the encode of chunk k.  All chunks belong to ONE
         // job (one descriptor array, one output stream); a later launch looks back into the
         // descriptors and symbols of the earlier ones.

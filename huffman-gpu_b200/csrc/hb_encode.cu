@@ -11,9 +11,9 @@
  * instruction issue, not by HBM, so everything is arranged to spend as few issue slots per symbol
  * as possible and to never leave a warp waiting on another one:
  *
- *   - one persistent CTA per SM: 16 autonomous WORKER warps + 1 SCOUT warp.  Tiles of 16 KiB are
- *     handed out by an atomic ticket counter; a worker warp owns a 1 KiB chunk of each tile
- *     (32 contiguous symbols per lane, one 256-bit load, prefetched one tile ahead);
+ *   - one persistent CTA per SM: 16 autonomous WORKER warps, a PUBLISHER warp and a RESOLVER warp.
+ *     Tiles of 16 KiB are handed out by an atomic ticket counter; a worker warp owns a 1 KiB chunk
+ *     of each tile (32 contiguous symbols per lane, one 256-bit load, prefetched one tile ahead);
  *   - the codebook lives in shared memory at a 256-byte stride per symbol, replicated per lane:
  *     ONE byte-permute builds the whole lookup address (symbol -> byte 1, lane*4 -> byte 0) and
  *     the lookup is bank-conflict free for any symbol distribution.  An entry is
@@ -28,15 +28,23 @@
  *     the left lane hands its partial tail word to the right one through a shuffle -- no
  *     shared-memory atomics, no zeroing.  Chunks that break the rules (ragged end of the input,
  *     zero-length codes, a group of 32+ bits) are re-encoded symbol by symbol with atomicOr;
- *   - workers never synchronise with each other.  They post their chunk's bit count to the scout,
- *     which publishes the tile aggregate and resolves the tile's global bit offset by a decoupled
- *     look-back over 64-bit descriptors {epoch, status, 48-bit count} while the workers are
- *     already encoding the next tile (staging is double buffered; mbarriers carry the hand-offs);
- *   - one tile later each worker copies its own staging region out, coalesced, with one funnel
+ *   - workers never synchronise with each other.  They post their chunk's bit count; the publisher
+ *     sums the 16 counts and publishes the tile aggregate at once (it never waits on other CTAs, so
+ *     there is no convoy).  Global bit offsets come from a decoupled look-back over a FENWICK TREE
+ *     instead of a flat descriptor array: with 148 tiles in flight and a new tile every ~7 cycles
+ *     GPU-wide, a classic look-back (every tile re-reading all of its ~148 unresolved predecessors,
+ *     again on every poll) turns a handful of descriptor lines into an L2 hot spot.  Here a tile adds
+ *     {1, bits} with one fire-and-forget 64-bit red.add to the <= log2(n) tree nodes that cover it,
+ *     and the resolver of a later tile reads the <= log2(n) nodes that tile its prefix; a node is
+ *     final when its count equals the number of tiles it covers.  O(log n) traffic per tile, no
+ *     serial chain, no scanner, and nothing to reset: each job zeroes the tree of the next one;
+ *     all of this runs while the workers are already encoding the next tiles (staging is a ring
+ *     of 3 slots; mbarriers carry every hand-off);
+ *   - two tiles later each worker copies its own staging region out, coalesced, with one funnel
  *     shift per word to the global phase.  An output word that straddles two chunks belongs to
  *     the right-hand chunk, which takes the missing (< 32) bits from a tiny carry ring; for the
- *     first chunk of a tile the scout re-derives them from the symbols just before the tile, so
- *     there is no inter-CTA data dependency, no atomics on the output and no memset of it.
+ *     first chunk of a tile the resolver re-derives them from the symbols just before the tile,
+ *     so there is no inter-CTA data dependency, no atomics on the output and no memset of it.
  */
 #include "hb_kernels.cuh"
 
@@ -45,40 +53,69 @@ namespace {
 
 constexpr int kW = kEncWorkers;
 constexpr int S = kSymPerThread;
-constexpr int kSlotBytes = 256;                         // table stride per symbol
-constexpr int kTabWords = 256 * kSlotBytes / 4;         // 64 KiB
+constexpr int kPublisherWarp = kW;
+constexpr int kResolverWarp = kW + 1;
+constexpr int kSlotStride = 256;                        // table stride per symbol (bytes)
+constexpr int kTabBytes = 256 * kSlotStride;            // 64 KiB
 constexpr unsigned long long kNoTile = ~0ULL;
+// Fenwick node = [63:44] tiles counted | [43:0] bits summed
+constexpr int kTreeCountShift = 44;
+constexpr unsigned long long kTreeOne = 1ULL << kTreeCountShift;
+constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 
 // Shared-memory map.  The table must start on a 64 KiB boundary of the CTA's shared window so that
 // the byte permute can produce a complete lookup address (window address bytes 2..3 are constants).
 // The window starts with kSmemReserved bytes owned by the system, so the dynamic block is laid out as
-//   [staging slot 0 | pad] up to the boundary, [table 64 KiB], [staging slot 1], [control block].
+//   [staging slot 0 | pad] up to the boundary, [table 64 KiB], [staging slots 1..NS-1], [control block].
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
 constexpr uint32_t kTabOffset = 65536 - kSmemReserved;  // table offset inside the dynamic block
+constexpr int kMaxSlots = 3;
 
 template <bool WIDE>
 struct Geo {
+    static constexpr int NS = WIDE ? 2 : 3;             // staging slots = tiles a worker may run ahead
     // a chunk of 32*S symbols can emit at most 32*S*max_len bits (max_len 24 packed, 31 wide)
     static constexpr int kRegionWords = S * (WIDE ? 31 : 24);
     static constexpr uint32_t kSlotBytes = kW * kRegionWords * 4;
-    static constexpr uint32_t kSlot1Offset = kTabOffset + kTabWords * 4;
-    static constexpr uint32_t kCtrlOffset = kSlot1Offset + kSlotBytes;
+    static constexpr uint32_t kSlot1Offset = kTabOffset + kTabBytes;
+    static constexpr uint32_t kCtrlOffset = kSlot1Offset + (NS - 1) * kSlotBytes;
     static_assert(kSlotBytes <= kTabOffset, "staging slot 0 must fit below the table");
+    __device__ static __forceinline__ uint32_t slot_offset(uint32_t slot)
+    {
+        return slot ? kSlot1Offset + (slot - 1u) * kSlotBytes : 0u;
+    }
 };
 
 struct Ctrl {
-    unsigned long long bar_sums[2];     // workers -> scout: chunk bit counts of tile k posted
-    unsigned long long bar_emit[2];     // workers -> workers: chunk carries of tile k posted
-    unsigned long long bar_prefix[2];   // scout -> workers: global offset of tile k resolved
-    unsigned long long bar_tile[4];     // scout -> workers: ring[k & 3] holds the k-th tile id
+    unsigned long long bar_sums[kMaxSlots];     // workers -> publisher: chunk bit counts of tile k posted
+    unsigned long long bar_agg[kMaxSlots];      // publisher -> resolver: aggregate of tile k published
+    unsigned long long bar_prefix[kMaxSlots];   // resolver -> workers: global offset of tile k resolved
+    unsigned long long bar_emit[kMaxSlots];     // workers -> workers: chunk carries of tile k posted
+    unsigned long long bar_tile[4];             // publisher -> workers: ring[k & 3] holds the k-th tile id
     unsigned long long ring[4];
-    unsigned long long prefix[2];
-    uint32_t prev[2];
-    uint32_t flags[2];
-    uint32_t woff[2][kW];
-    uint32_t sums[2][kW];
-    uint32_t carry_val[4][kW];
-    uint32_t carry_cnt[4][kW];
+    unsigned long long sq[8];                   // the same sequence for the resolver (longer lived)
+    unsigned long long prefix[kMaxSlots];
+    uint32_t prev[kMaxSlots];
+    uint32_t flags[kMaxSlots];
+    uint32_t btile[kMaxSlots];
+    uint32_t woff[kMaxSlots][kW];
+    uint32_t sums[kMaxSlots][kW];
+    uint32_t carry_val[8][kW];
+    uint32_t carry_cnt[8][kW];
+};
+
+// position k of a CTA's tile sequence -> staging slot k % NS and mbarrier parity (k / NS) & 1
+template <int NS>
+struct Cursor {
+    uint32_t k = 0, slot = 0, par = 0;
+    __device__ __forceinline__ void next()
+    {
+        k++;
+        if (++slot == (uint32_t)NS) {
+            slot = 0;
+            par ^= 1u;
+        }
+    }
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------
@@ -114,9 +151,9 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v)
+__device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // one 256-bit load per lane: a warp reads 1 KiB contiguous, streamed past L1 (LDG.E.256 on sm_100a)
 __device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t (&w)[8])
@@ -126,11 +163,25 @@ __device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t (&w)[8]
                    "=r"(w[7])
                  : "l"(p));
 }
-__device__ __forceinline__ unsigned long long pack_desc(uint32_t epoch, unsigned long long status,
-                                                        unsigned long long bits)
-{
-    return ((unsigned long long)epoch << 50) | (status << kDescValueBits) | (bits & kDescValueMask);
-}
+// ---- optional cycle accounting ($HB_PROFILE=1; one branch per tile when off) ----------------------------
+enum { kProfWaitTile = 0, kProfWaitPrefix, kProfWorker, kProfWaitSums, kProfWaitAgg, kProfLookback,
+       kProfBitsBefore, kProfResolver, kProfTiles, kProfPolls, kProfPass1, kProfEmit, kProfCopy, kProfCount };
+struct Prof {
+    unsigned long long v[kProfCount];
+    bool on;
+    __device__ Prof(const EncParams &p, bool enable) : on(p.prof != nullptr && enable)
+    {
+        for (int i = 0; i < kProfCount; i++) v[i] = 0;
+    }
+    __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
+    __device__ __forceinline__ void add(int i, long long t0) { if (on) v[i] += (unsigned long long)(clock64() - t0); }
+    __device__ void flush(const EncParams &p, uint32_t lane)
+    {
+        if (on && lane == 0)
+            for (int i = 0; i < kProfCount; i++)
+                if (v[i]) atomicAdd(&p.prof[i], v[i]);
+    }
+};
 
 // ---- codebook in shared memory ---------------------------------------------------------------------
 // slot(sym) = 256 bytes: words 0..31 = the entry replicated per lane; wide tables keep the length in
@@ -151,7 +202,7 @@ template <bool WIDE>
 __device__ __forceinline__ void fetch_entry(uint32_t tab_s, uint32_t sym, uint32_t lane, uint32_t &c,
                                             uint32_t &len)
 {
-    const uint32_t addr = tab_s + sym * kSlotBytes + lane * 4u;
+    const uint32_t addr = tab_s + sym * kSlotStride + lane * 4u;
     c = tab_ld(addr);
     len = WIDE ? tab_ld_len(addr) : (c & 0xFFu);
 }
@@ -177,12 +228,12 @@ __device__ __forceinline__ unsigned long long byte_of_symbol(unsigned long long 
     return (idx & ~3ULL) + (3ULL - (idx & 3ULL));
 }
 
-// ---- the last `need` (< 32) stream bits that precede symbol index `first_sym` ---------------------
+// ---- the last `need` (< 32) stream bits that precede symbol index `first_sym` (general, slow) --------
 // Executed by one full warp.  Walks backwards 32 symbols at a time until `need` bits are covered or
 // the buffer start is reached (then the missing high bits are zero: the start_bit phase of a shard).
 template <bool WIDE>
-__device__ uint32_t bits_before(const EncParams &p, uint32_t tab_s,
-                                unsigned long long first_sym, uint32_t need, uint32_t lane)
+__device__ uint32_t bits_before(const EncParams &p, uint32_t tab_s, unsigned long long first_sym,
+                                uint32_t need, uint32_t lane)
 {
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     uint32_t acc = 0, have = 0;
@@ -210,19 +261,24 @@ __device__ uint32_t bits_before(const EncParams &p, uint32_t tab_s,
     return acc;
 }
 
-// ---- scout warp: tickets, aggregates, look-back -------------------------------------------------------
+// ---- publisher warp: tickets and tile aggregates ---------------------------------------------------------
+// Never waits on another CTA: as soon as the 16 chunk counts of a tile are in, their sum is published,
+// whatever state this CTA's own look-backs are in.
 template <bool WIDE>
-__device__ void scout(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t lane)
+__device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
 {
+    constexpr int NS = Geo<WIDE>::NS;
     bool ended = false;
-    // k-th tile of this CTA -> ring[k & 3]
-    auto post = [&](uint32_t k) -> unsigned long long {
+    auto draw = [&]() -> unsigned long long {            // raw ticket; its latency is hidden until first use
+        unsigned long long tk = 0;
+        if (lane == 0 && !ended) tk = atomicAdd(p.ticket, 1ULL);
+        return tk;
+    };
+    // k-th tile of this CTA: ring[k & 3] for the workers, sq[k & 7] for the resolver
+    auto post = [&](uint32_t k, unsigned long long raw) -> unsigned long long {
         unsigned long long t = kNoTile;
         if (!ended) {
-            unsigned long long tk = 0;
-            if (lane == 0) tk = atomicAdd(p.ticket, 1ULL);
-            tk = __shfl_sync(0xFFFFFFFFu, tk, 0);
-            t = tk - p.ticket_base + p.first_tile;
+            t = __shfl_sync(0xFFFFFFFFu, raw, 0) - p.ticket_base + p.first_tile;
             if (t >= p.end_tile) {
                 t = kNoTile;
                 ended = true;           // exactly one ticket past the end per CTA
@@ -230,20 +286,24 @@ __device__ void scout(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t l
         }
         if (lane == 0) {
             ctrl->ring[k & 3u] = t;
+            ctrl->sq[k & 7u] = t;
             mbar_arrive(&ctrl->bar_tile[k & 3u]);
         }
         return t;
     };
 
-    unsigned long long t_cur = post(0);
-    unsigned long long t_next = post(1);
-    for (uint32_t k = 0; t_cur != kNoTile; k++) {
-        const uint32_t slot = k & 1u;
-        const unsigned long long tile = t_cur;
-        mbar_wait(&ctrl->bar_sums[slot], (k >> 1) & 1u);
+    unsigned long long t_cur = post(0, draw());
+    unsigned long long t_next = post(1, draw());
+    for (Cursor<NS> c;; c.next()) {
+        if (t_cur == kNoTile) {
+            if (lane == 0) mbar_arrive(&ctrl->bar_agg[c.slot]);      // wakes the resolver, which then stops too
+            break;
+        }
+        const unsigned long long raw = draw();                       // position k + 2
+        mbar_wait(&ctrl->bar_sums[c.slot], c.par);
 
         // exclusive scan of the 16 chunk bit counts
-        const uint32_t n = (lane < (uint32_t)kW) ? ctrl->sums[slot][lane] : 0u;
+        const uint32_t n = (lane < (uint32_t)kW) ? ctrl->sums[c.slot][lane] : 0u;
         uint32_t incl = n;
 #pragma unroll
         for (int d = 1; d < kW; d <<= 1) {
@@ -251,110 +311,174 @@ __device__ void scout(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t l
             if (lane >= (uint32_t)d) incl += v;
         }
         const uint32_t btile = __shfl_sync(0xFFFFFFFFu, incl, kW - 1);
-        if (lane < (uint32_t)kW) ctrl->woff[slot][lane] = incl - n;
-
-        // publish early: successors only need the count, not our data
+        if (lane < (uint32_t)kW) ctrl->woff[c.slot][lane] = incl - n;
+        // Fenwick update: lane j adds {1 tile, btile bits} to the j-th node above tile t_cur (1-based index
+        // t_cur + 1, then repeatedly + lowbit).  Nodes at or beyond the last tile are never read: skip them.
+        {
+            unsigned long long i = t_cur + 1ULL;
+            for (uint32_t j = 0; j < lane && i < p.n_tiles; j++) i += i & (0ULL - i);
+            if (i < p.n_tiles) red_add_u64(&p.tree[i], kTreeOne | (unsigned long long)btile);
+        }
+        __syncwarp();
         if (lane == 0) {
-            if (tile == 0)
-                st_relaxed_u64(&p.desc[0], pack_desc(p.epoch, kStatusPrefix, p.start_bit + btile));
-            else
-                st_relaxed_u64(&p.desc[tile], pack_desc(p.epoch, kStatusAggregate, btile));
+            ctrl->btile[c.slot] = btile;
+            mbar_arrive(&ctrl->bar_agg[c.slot]);
         }
         // every worker is past pass 1 of tile k, so ring[(k + 2) & 3] (tile k - 2) is dead
         t_cur = t_next;
-        t_next = post(k + 2);
-
-        // ---------------- decoupled look-back ----------------
-        unsigned long long excl;
-        if (tile == 0) {
-            excl = p.start_bit;
-        } else {
-            excl = 0;
-            long long look = (long long)tile - 1;
-            for (;;) {
-                const long long idx = look - (long long)lane;
-                const unsigned long long d =
-                    (idx >= 0) ? ld_relaxed_u64(&p.desc[idx]) : pack_desc(p.epoch, kStatusPrefix, 0);
-                const uint32_t st =
-                    ((uint32_t)(d >> 50) == p.epoch) ? (uint32_t)((d >> kDescValueBits) & 3u) : 0u;
-                const uint32_t pmask = __ballot_sync(0xFFFFFFFFu, st == kStatusPrefix);
-                const uint32_t xmask = __ballot_sync(0xFFFFFFFFu, st == 0u);
-                const uint32_t first_p = pmask ? (uint32_t)(__ffs(pmask) - 1) : 32u;
-                const uint32_t need = (first_p >= 31u) ? 0xFFFFFFFFu : ((2u << first_p) - 1u);
-                if (xmask & need) {
-                    __nanosleep(20);
-                    continue;                               // a needed predecessor has not published yet
-                }
-                unsigned long long v = ((need >> lane) & 1u) ? (d & kDescValueMask) : 0ULL;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                excl += v;
-                if (first_p < 32u) break;
-                look -= 32;
-            }
-            if (lane == 0)
-                st_relaxed_u64(&p.desc[tile], pack_desc(p.epoch, kStatusPrefix, excl + btile));
-        }
-        const uint32_t sh = (uint32_t)(excl & 31ULL);
-        uint32_t prev = 0;
-        // nothing precedes the job's first bit: the start_bit phase is zero-filled (also keeps
-        // all-zero-length codebooks from walking the whole input backwards)
-        if (sh != 0 && tile != 0 && excl != p.start_bit)
-            prev = bits_before<WIDE>(p, tab_s, tile * (unsigned long long)kTileBytes, sh, lane);
-        if (lane == 0) {
-            ctrl->prefix[slot] = excl;
-            ctrl->prev[slot] = prev;
-            ctrl->flags[slot] = (tile == p.n_tiles - 1 ? 1u : 0u) | (tile == p.end_tile - 1 ? 2u : 0u);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ctrl->bar_prefix[slot]);
+        t_next = post(c.k + 2u, raw);
     }
 }
 
-// ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
-__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *st, uint32_t k,
-                                         uint32_t n, uint32_t warp, uint32_t lane)
+// ---- resolver warp: look-back over the Fenwick tree --------------------------------------------------------
+template <bool WIDE>
+__device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t lane)
 {
-    const uint32_t slot = k & 1u;
-    mbar_wait(&ctrl->bar_emit[slot], (k >> 1) & 1u);
-    mbar_wait(&ctrl->bar_prefix[slot], (k >> 1) & 1u);
+    constexpr int NS = Geo<WIDE>::NS;
+    Prof prof(p, true);
+    const long long t_all = prof.now();
+    const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
+    // the symbol `lane + 1` places before a tile, for the (< 32) stream bits that precede it
+    auto tail_symbol = [&](unsigned long long t) -> uint32_t {
+        if (t == kNoTile) return 0u;
+        const long long idx = (long long)(t * (unsigned long long)kTileBytes) - 1 - (long long)lane;
+        return idx >= 0 ? (uint32_t)bytes[byte_of_symbol((unsigned long long)idx)] : 0u;
+    };
+
+    uint32_t sym = 0;
+    for (Cursor<NS> c;; c.next()) {
+        long long t0 = prof.now();
+        mbar_wait(&ctrl->bar_agg[c.slot], c.par);
+        prof.add(kProfWaitAgg, t0);
+        const unsigned long long tile = ctrl->sq[c.k & 7u];
+        if (tile == kNoTile) break;
+        if (c.k == 0) sym = tail_symbol(tile);
+        prof.v[kProfTiles]++;
+
+        // ---------------- look-back: the <= log2(n) tree nodes that tile the prefix [0, tile) ----------------
+        // lane j owns node i_j (i_0 = tile, i_{j+1} = i_j - lowbit(i_j)), final once it has counted lowbit(i_j) tiles
+        t0 = prof.now();
+        unsigned long long excl = 0;
+        {
+            unsigned long long i = tile;
+            for (uint32_t j = 0; j < lane && i; j++) i &= i - 1ULL;
+            const unsigned long long want = (i & (0ULL - i)) << kTreeCountShift;
+            unsigned long long v = 0;
+            bool pending = i != 0;
+            for (;;) {
+                if (pending) {
+                    v = ld_relaxed_u64(&p.tree[i]);
+                    pending = (v & ~kTreeSumMask) != want;
+                }
+                prof.v[kProfPolls]++;
+                if (!__any_sync(0xFFFFFFFFu, pending)) break;
+                __nanosleep(64);
+            }
+            v &= kTreeSumMask;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            excl = p.start_bit + v;
+        }
+        if (tile == p.end_tile - 1 && lane == 0) p.result->bits_end = excl + ctrl->btile[c.slot];
+        prof.add(kProfLookback, t0);
+
+        // ---------------- the (excl & 31) stream bits just before the tile ----------------
+        t0 = prof.now();
+        const uint32_t sh = (uint32_t)(excl & 31ULL);
+        uint32_t prev = 0;
+        // nothing precedes the job's first bit: the start_bit phase is zero-filled (this also keeps
+        // all-zero-length codebooks from walking the whole input backwards)
+        if (sh != 0 && tile != 0 && excl != p.start_bit) {
+            const unsigned long long first_sym = tile * (unsigned long long)kTileBytes;
+            uint32_t cwl, len;
+            fetch_entry<WIDE>(tab_s, sym, lane, cwl, len);
+            if ((unsigned long long)lane >= first_sym) len = 0;
+            const uint32_t cw = len ? (cwl >> (32u - len)) : 0u;
+            uint32_t incl = len;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t nn = __shfl_up_sync(0xFFFFFFFFu, incl, dd);
+                if (lane >= (uint32_t)dd) incl += nn;
+            }
+            const uint32_t pos = incl - len;
+            prev = __reduce_or_sync(0xFFFFFFFFu, (pos < 32u) ? (cw << pos) : 0u);
+            const uint32_t have = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            // fewer than `sh` bits in 32 symbols (zero-length codes): walk further back
+            if (have < sh && first_sym > 32ULL) prev = bits_before<WIDE>(p, tab_s, first_sym, sh, lane);
+        }
+        if (lane == 0) {
+            ctrl->prefix[c.slot] = excl;
+            ctrl->prev[c.slot] = prev;
+            ctrl->flags[c.slot] = (tile == p.n_tiles - 1) ? 1u : 0u;
+            mbar_arrive(&ctrl->bar_prefix[c.slot]);
+        }
+        // the next tile's tail symbols: the load has a whole tile to land (sq[k+1] was posted before agg[k])
+        sym = tail_symbol(ctrl->sq[(c.k + 1u) & 7u]);
+        prof.add(kProfBitsBefore, t0);
+    }
+    prof.add(kProfResolver, t_all);
+    prof.flush(p, lane);
+}
+
+// ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
+template <int NS>
+__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *st,
+                                         const Cursor<NS> &c, uint32_t n, uint32_t warp, uint32_t lane,
+                                         Prof &prof)
+{
+    long long t0 = prof.now();
+    mbar_wait(&ctrl->bar_emit[c.slot], c.par);
+    mbar_wait(&ctrl->bar_prefix[c.slot], c.par);
+    prof.add(kProfWaitPrefix, t0);
+    t0 = prof.now();
 
     // the (< 32) bits that precede this chunk: neighbours' carries, then the tile's `prev`
     uint32_t cin = 0, have = 0;
     for (int r = (int)warp - 1; r >= 0 && have < 31u; r--) {
-        cin |= ctrl->carry_val[k & 3u][r] << have;
-        have += ctrl->carry_cnt[k & 3u][r];
+        cin |= ctrl->carry_val[c.k & 7u][r] << have;
+        have += ctrl->carry_cnt[c.k & 7u][r];
     }
-    if (have < 31u) cin |= ctrl->prev[slot] << have;
+    if (have < 31u) cin |= ctrl->prev[c.slot] << have;
 
-    const unsigned long long B = ctrl->prefix[slot] + ctrl->woff[slot][warp];
-    const uint32_t flags = ctrl->flags[slot];
+    const unsigned long long B = ctrl->prefix[c.slot] + ctrl->woff[c.slot][warp];
     const uint32_t sh = (uint32_t)(B & 31ULL);
     const unsigned long long g0 = B >> 5;
     const unsigned long long end = B + n;
-    const uint32_t nfull = (uint32_t)((end >> 5) - g0);
-    const bool last = (flags & 1u) && warp == (uint32_t)kW - 1;   // the job's final word(s)
-    const uint32_t nwrite = nfull + (last ? 1u : 0u);
-    const uint32_t nstage = (n + 31u) >> 5;
-    bool spill = false;
-    for (uint32_t j = lane; j < nwrite; j += 32u) {
-        const uint32_t cur = (j < nstage) ? st[j] : 0u;
-        const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? st[j - 1] : 0u);
-        const uint32_t v = __funnelshift_r(cur, before, sh);
-        if (g0 + j < p.out_cap_words)
-            p.out[g0 + j] = v;
-        else if (!(last && j == nfull && (end & 31ULL) == 0))      // the courtesy zero word may not fit
-            spill = true;
+    const uint32_t nfull = (uint32_t)((end >> 5) - g0);        // words whose last bit is ours (<= ceil(n/32))
+    const bool last = ctrl->flags[c.slot] && warp == (uint32_t)kW - 1;   // the job's final word(s)
+    if (!last && g0 + nfull <= p.out_cap_words) {
+        // common case: every word this chunk owns comes from two neighbouring staged words
+        uint32_t *out = p.out + g0;
+#pragma unroll 2
+        for (uint32_t j = lane; j < nfull; j += 32u) {
+            const uint32_t before = j ? st[j - 1u] : cin;
+            out[j] = __funnelshift_r(st[j], before, sh);
+        }
+    } else {
+        const uint32_t nwrite = nfull + (last ? 1u : 0u);
+        const uint32_t nstage = (n + 31u) >> 5;
+        bool spill = false;
+        for (uint32_t j = lane; j < nwrite; j += 32u) {
+            const uint32_t cur = (j < nstage) ? st[j] : 0u;
+            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? st[j - 1] : 0u);
+            const uint32_t v = __funnelshift_r(cur, before, sh);
+            if (g0 + j < p.out_cap_words)
+                p.out[g0 + j] = v;
+            else if (!(last && j == nfull && (end & 31ULL) == 0))      // the courtesy zero word may not fit
+                spill = true;
+        }
+        if (spill) p.result->overflow = 1ULL;
     }
-    if (spill) p.result->overflow = 1ULL;
-    if ((flags & 2u) && warp == (uint32_t)kW - 1 && lane == 0) p.result->bits_end = end;
+    prof.add(kProfCopy, t0);
 }
 
 // ---- worker warp ----------------------------------------------------------------------------------------
 template <int G, bool WIDE, bool CHECK>
-__device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uint32_t *stage1, Ctrl *ctrl,
-                       uint32_t warp, uint32_t lane)
+__device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_base, Ctrl *ctrl, uint32_t warp,
+                       uint32_t lane)
 {
+    constexpr int NS = Geo<WIDE>::NS;
+    constexpr int LAG = NS - 1;                               // copy-out trails the encode by LAG tiles
     constexpr int NG = (S + G - 1) / G;
     constexpr int RW = Geo<WIDE>::kRegionWords;
     // byte 0 = lane*4, bytes 1..2 = bytes 2..3 of the table's window address (prmt source b)
@@ -362,28 +486,41 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uin
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     const unsigned long long n_bytes = p.n_words * 4ULL;
 
-    auto region = [&](uint32_t slot) { return (slot ? stage1 : stage0) + warp * RW; };
-
-    uint32_t w[8], wn[8];
-    mbar_wait(&ctrl->bar_tile[0], 0);
-    unsigned long long tile = ctrl->ring[0];
+    auto region = [&](uint32_t slot) {
+        return reinterpret_cast<uint32_t *>(smem_base + Geo<WIDE>::slot_offset(slot)) + warp * RW;
+    };
     auto chunk_word0 = [&](unsigned long long t) {
         return t * (unsigned long long)kTileWords + warp * (unsigned long long)(kChunkBytes / 4);
     };
     auto chunk_full = [&](unsigned long long t) {
         return chunk_word0(t) + (unsigned long long)(kChunkBytes / 4) <= p.n_words;
     };
+
+    Prof prof(p, warp == 0);
+    const long long t_worker = prof.now();
+    uint32_t w[8], wn[8];
+    mbar_wait(&ctrl->bar_tile[0], 0);
+    unsigned long long tile = ctrl->ring[0];
     if (tile != kNoTile && chunk_full(tile)) ld_stream_v8(p.in + chunk_word0(tile) + lane * 8u, w);
 
-    uint32_t n_prev = 0;
-    uint32_t k = 0;
-    for (; tile != kNoTile; k++) {
-        const uint32_t slot = k & 1u;
-        uint32_t *st = region(slot);
+    uint32_t n_hist[LAG];                                     // bit counts of the tiles awaiting copy-out
+#pragma unroll
+    for (int i = 0; i < LAG; i++) n_hist[i] = 0;
+    Cursor<NS> c, cc;                                         // encode position, copy-out position
+    for (; tile != kNoTile; c.next()) {
+        uint32_t *st = region(c.slot);
 
         // ---------------- prefetch the next tile's chunk ----------------
-        mbar_wait(&ctrl->bar_tile[(k + 1) & 3u], ((k + 1) >> 2) & 1u);
-        const unsigned long long tnext = ctrl->ring[(k + 1) & 3u];
+        // Scoreboard slots count per instruction, not per register: the load below and the one that filled
+        // `w` a tile ago are the same SASS instruction, so the first read of `w` would also wait for the
+        // NEW load.  Reading `w` here, before the new load is issued, only waits for the old one.
+#pragma unroll
+        for (int i = 0; i < 8; i++) asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
+        long long t0 = prof.now();
+        mbar_wait(&ctrl->bar_tile[(c.k + 1u) & 3u], ((c.k + 1u) >> 2) & 1u);
+        prof.add(kProfWaitTile, t0);
+        t0 = prof.now();
+        const unsigned long long tnext = ctrl->ring[(c.k + 1u) & 3u];
         if (tnext != kNoTile && chunk_full(tnext)) ld_stream_v8(p.in + chunk_word0(tnext) + lane * 8u, wn);
 
         // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
@@ -399,9 +536,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uin
                 // {lane*4, symbol, table address bytes 2..3}: the whole lookup address in one prmt
                 const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
                 if (WIDE) {
-                    const uint32_t c = tab_ld(off);
+                    const uint32_t cwl = tab_ld(off);
                     const uint32_t l = tab_ld_len(off);
-                    lo = __funnelshift_l(c, lo, l);
+                    lo = __funnelshift_l(cwl, lo, l);
                     gs += l;
                 } else {
                     const uint32_t e = tab_ld(off);
@@ -420,14 +557,16 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uin
 #pragma unroll 1
             for (int i = 0; i < S; i++) {
                 if (sym0 + i < n_bytes) {
-                    uint32_t c, l;
-                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, c, l);
+                    uint32_t cwl, l;
+                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
                     bt += l;
                 }
             }
 #pragma unroll
             for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
         }
+        prof.add(kProfPass1, t0);
+        t0 = prof.now();
 
         // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
         uint32_t incl = bt;
@@ -439,8 +578,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uin
         const uint32_t q0 = incl - bt;
         const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (lane == 31) {
-            ctrl->sums[slot][warp] = n;
-            mbar_arrive(&ctrl->bar_sums[slot]);
+            ctrl->sums[c.slot][warp] = n;
+            mbar_arrive(&ctrl->bar_sums[c.slot]);
         }
 
         // ---------------- pass 2: bits -> this warp's staging region (chunk-relative alignment) ----------------
@@ -475,10 +614,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uin
 #pragma unroll 1
             for (int i = 0; i < S; i++) {
                 if (sym0 + i < n_bytes) {
-                    uint32_t c, l;
-                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, c, l);
+                    uint32_t cwl, l;
+                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
                     if (l) {
-                        const uint32_t ln = __funnelshift_l(c, lo, l);
+                        const uint32_t ln = __funnelshift_l(cwl, lo, l);
                         const uint32_t qn = q + l;
                         if ((qn ^ q) & ~31u)
                             atomicOr(&st[(qn >> 5) - 1u], __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
@@ -500,21 +639,36 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *stage0, uin
                 const uint32_t w1 = st[a], w0 = a ? st[a - 1u] : 0u;
                 val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
             }
-            ctrl->carry_val[k & 3u][warp] = val;
-            ctrl->carry_cnt[k & 3u][warp] = n < 31u ? n : 31u;
-            mbar_arrive(&ctrl->bar_emit[slot]);
+            ctrl->carry_val[c.k & 7u][warp] = val;
+            ctrl->carry_cnt[c.k & 7u][warp] = n < 31u ? n : 31u;
+            mbar_arrive(&ctrl->bar_emit[c.slot]);
         }
+        prof.add(kProfEmit, t0);
 
-        // ---------------- copy-out of the PREVIOUS tile (its look-back had a whole tile of slack) ----------------
-        if (k > 0) copy_out(p, ctrl, region((k - 1u) & 1u), k - 1u, n_prev, warp, lane);
+        // ---------------- copy-out of tile k - LAG (its look-back had LAG tiles of slack) ----------------
+        if (c.k >= (uint32_t)LAG) {
+            copy_out<NS>(p, ctrl, region(cc.slot), cc, n_hist[LAG - 1], warp, lane, prof);
+            cc.next();
+        }
+#pragma unroll
+        for (int i = LAG - 1; i > 0; i--) n_hist[i] = n_hist[i - 1];
+        n_hist[0] = n;
 
         __syncwarp();
-        n_prev = n;
         tile = tnext;
 #pragma unroll
         for (int i = 0; i < 8; i++) w[i] = wn[i];
     }
-    if (k > 0) copy_out(p, ctrl, region((k - 1u) & 1u), k - 1u, n_prev, warp, lane);
+    // drain: positions cc.k .. c.k-1 are still staged; the count of position c.k-1-i is n_hist[i]
+#pragma unroll
+    for (int i = LAG - 1; i >= 0; i--) {
+        if (c.k > (uint32_t)i && cc.k == c.k - 1u - (uint32_t)i) {
+            copy_out<NS>(p, ctrl, region(cc.slot), cc, n_hist[i], warp, lane, prof);
+            cc.next();
+        }
+    }
+    prof.add(kProfWorker, t_worker);
+    prof.flush(p, lane);
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -524,8 +678,6 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     extern __shared__ __align__(1024) uint32_t smem[];
     unsigned char *base = reinterpret_cast<unsigned char *>(smem);
     uint32_t *tab = reinterpret_cast<uint32_t *>(base + kTabOffset);
-    uint32_t *stage0 = smem;
-    uint32_t *stage1 = reinterpret_cast<uint32_t *>(base + Geo<WIDE>::kSlot1Offset);
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(base + Geo<WIDE>::kCtrlOffset);
     const uint32_t tab_s = smem_addr(tab);
     if (tab_s & 0xFFFFu) {
@@ -538,21 +690,29 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
 
+    // the tree the NEXT job on this context will use (nothing reads or writes it during this launch)
+    for (unsigned long long i = (unsigned long long)blockIdx.x * kEncThreads + tid; i < p.zero_count;
+         i += (unsigned long long)gridDim.x * kEncThreads)
+        p.tree_zero[i] = 0ULL;
     fill_table<WIDE>(tab, p.table, tid);
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kMaxSlots; i++) {
             mbar_init(&ctrl->bar_sums[i], kW);
             mbar_init(&ctrl->bar_emit[i], kW);
+            mbar_init(&ctrl->bar_agg[i], 1);
             mbar_init(&ctrl->bar_prefix[i], 1);
         }
         for (int i = 0; i < 4; i++) mbar_init(&ctrl->bar_tile[i], 1);
     }
     __syncthreads();
 
-    if (warp == (uint32_t)kW)
-        scout<WIDE>(p, tab_s, ctrl, lane);
+    if (warp == (uint32_t)kPublisherWarp)
+        publisher<WIDE>(p, ctrl, lane);
+    else if (warp == (uint32_t)kResolverWarp)
+        resolver<WIDE>(p, tab_s, ctrl, lane);
+
     else
-        worker<G, WIDE, CHECK>(p, tab_s, stage0, stage1, ctrl, warp, lane);
+        worker<G, WIDE, CHECK>(p, tab_s, base, ctrl, warp, lane);
 }
 
 template <bool WIDE>

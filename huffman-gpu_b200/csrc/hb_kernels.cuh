@@ -10,21 +10,14 @@
 namespace hb {
 
 // ---- geometry of the single-pass encoder ---------------------------------------------------------
-// One persistent CTA per SM: kEncWorkers worker warps + 1 scout warp.  A tile is the CTA's unit of
+// One persistent CTA per SM: kEncWorkers worker warps + a publisher warp + a resolver warp.  A tile is the CTA's unit of
 // work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
 constexpr int kEncWorkers = 16;
-constexpr int kEncThreads = (kEncWorkers + 1) * 32;
+constexpr int kEncThreads = (kEncWorkers + 2) * 32;
 constexpr int kSymPerThread = 32;                                     // symbols (bytes) per thread per tile
 constexpr int kChunkBytes = 32 * kSymPerThread;                       // one warp: 1 KiB
 constexpr int kTileBytes = kEncWorkers * kChunkBytes;                 // 16 KiB
 constexpr int kTileWords = kTileBytes / 4;
-
-// ---- decoupled look-back descriptor: [63:50] epoch | [49:48] status | [47:0] bits ---------------
-constexpr int kDescValueBits = 48;
-constexpr uint64_t kDescValueMask = (1ULL << kDescValueBits) - 1;
-constexpr uint64_t kStatusAggregate = 1;               // value = bits of this tile only
-constexpr uint64_t kStatusPrefix = 2;                  // value = bits up to and including this tile
-constexpr uint32_t kEpochMask = 0x3FFF;
 
 // Written by the kernel into mapped pinned host memory (zero-copy), read by the host after sync.
 struct EncResult {
@@ -41,12 +34,14 @@ struct EncParams {
     uint32_t *out;
     unsigned long long out_cap_words;
     unsigned long long start_bit;     // global bit position of the job's first bit
-    unsigned long long *desc;         // one descriptor per tile of the job
+    unsigned long long *tree;         // Fenwick tree over the job's tile bit counts, 1-based, n_tiles entries
+    unsigned long long *tree_zero;    // the tree of the next job: entries [0, zero_count) are cleared
+    unsigned long long zero_count;
     unsigned long long *ticket;       // monotonically increasing work counter (never reset)
     unsigned long long ticket_base;   // counter value at the start of this launch
-    uint32_t epoch;
     const uint32_t *table;            // packed: uint32[256]; wide: uint2[256] as uint32[512]
     EncResult *result;
+    unsigned long long *prof;         // optional cycle counters ($HB_PROFILE), else nullptr
 };
 
 // Encode kernel variants.

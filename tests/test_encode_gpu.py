@@ -351,7 +351,7 @@ def test_synth_device_matches_host(hb, enc, orc, torch_mod):
         d = synth_on_device(hb, enc, torch_mod, wl, n_bytes=1 << 20)
         assert np.array_equal(d.cpu().numpy(), orc.synth_fill(0, 1 << 20, wl.seed, wl.mode, wl.nbits, wl.thr))
     wl = hb.workloads.get("c4")
-    d = torch_mod.empty(1 << 16, dtype=torch.uint8, device="cuda")
+    d = torch_mod.empty(1 << 16, dtype=torch_mod.uint8, device="cuda")
     enc.synth_fill(d, wl, first=12345678)
     assert np.array_equal(d.cpu().numpy(),
                           orc.synth_fill(12345678, 1 << 16, wl.seed, wl.mode, wl.nbits, wl.thr))
@@ -366,7 +366,7 @@ def test_full_size_config_vs_oracle(hb, enc, orc, ref, torch_mod, name):
     assert int(hist.sum()) == wl.n_bytes
     cw, cl, max_len = hb.build_codebook(hist)
     bits_expected = hb.bits_from_hist(hist, cl)
-    d_out = torch_mod.empty(bits_expected // 32 + 2, dtype=torch.int32, device="cuda")
+    d_out = torch_mod.empty(bits_expected // 32 + 2, dtype=torch_mod.int32, device="cuda")
     d_out.fill_(0x5A5A5A5A)
     bits = enc.encode(d_in, cw, cl, d_out)
     assert bits == bits_expected
@@ -396,7 +396,7 @@ def test_c4_fibonacci_sample_and_properties(hb, enc, orc, torch_mod):
     g = [c for c in load_golden("codebooks.json") if c.get("name") == "c4_fibonacci"][0]
     assert cw.tolist() == g["codewords"] and cl.tolist() == g["codewordlens"]
     bits_expected = hb.bits_from_hist(hist, cl)
-    d_out = torch_mod.empty(bits_expected // 32 + 2, dtype=torch.int32, device="cuda")
+    d_out = torch_mod.empty(bits_expected // 32 + 2, dtype=torch_mod.int32, device="cuda")
     bits = big.encode(d_in, cw, cl, d_out)
     assert bits == bits_expected
     rng = np.random.default_rng(4)
