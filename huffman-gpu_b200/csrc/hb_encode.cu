@@ -38,10 +38,12 @@
  *     and the resolver of a later tile reads the <= log2(n) nodes that tile its prefix; a node is
  *     final when its count equals the number of tiles it covers.  O(log n) traffic per tile, no
  *     serial chain, no scanner, and nothing to reset: each job zeroes the tree of the next one;
- *     all of this runs while the workers are already encoding the next tiles (staging is a ring
- *     of 3 slots; mbarriers carry every hand-off);
- *   - two tiles later each worker copies its own staging region out, coalesced, with one funnel
- *     shift per word to the global phase.  An output word that straddles two chunks belongs to
+ *   - all of this runs while the workers are already encoding the next tiles: a worker stages its
+ *     chunks in a private shared-memory RING (9.5 KiB, allocated by actual size), so up to 8 tiles
+ *     can be between encode and copy-out and the latency of the look-back -- and its variance
+ *     across 148 CTAs -- never reaches the encode loop.  mbarriers carry every hand-off;
+ *   - as soon as a tile's offset is resolved each worker copies its own chunk out, coalesced, with
+ *     one funnel shift per word to the global phase.  An output word that straddles two chunks belongs to
  *     the right-hand chunk, which takes the missing (< 32) bits from a tiny carry ring; for the
  *     first chunk of a tile the resolver re-derives them from the symbols just before the tile,
  *     so there is no inter-CTA data dependency, no atomics on the output and no memset of it.
@@ -66,57 +68,40 @@ constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 // Shared-memory map.  The table must start on a 64 KiB boundary of the CTA's shared window so that
 // the byte permute can produce a complete lookup address (window address bytes 2..3 are constants).
 // The window starts with kSmemReserved bytes owned by the system, so the dynamic block is laid out as
-//   [staging slot 0 | pad] up to the boundary, [table 64 KiB], [staging slots 1..NS-1], [control block].
+//   [rings of workers 0..5 | pad] up to the boundary, [table 64 KiB], [rings of workers 6..15], [control].
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
 constexpr uint32_t kTabOffset = 65536 - kSmemReserved;  // table offset inside the dynamic block
-constexpr int kMaxSlots = 3;
-
-template <bool WIDE>
-struct Geo {
-    static constexpr int NS = WIDE ? 2 : 3;             // staging slots = tiles a worker may run ahead
-    // a chunk of 32*S symbols can emit at most 32*S*max_len bits (max_len 24 packed, 31 wide)
-    static constexpr int kRegionWords = S * (WIDE ? 31 : 24);
-    static constexpr uint32_t kSlotBytes = kW * kRegionWords * 4;
-    static constexpr uint32_t kSlot1Offset = kTabOffset + kTabBytes;
-    static constexpr uint32_t kCtrlOffset = kSlot1Offset + (NS - 1) * kSlotBytes;
-    static_assert(kSlotBytes <= kTabOffset, "staging slot 0 must fit below the table");
-    __device__ static __forceinline__ uint32_t slot_offset(uint32_t slot)
-    {
-        return slot ? kSlot1Offset + (slot - 1u) * kSlotBytes : 0u;
-    }
-};
+constexpr int kAhead = 4;                               // tile tickets drawn ahead of the slowest worker
+constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
+constexpr uint32_t kRingWords = 2432;                   // per worker; >= 3 worst-case packed chunks (3 * 768)
+constexpr int kRingsBelow = 6;                          // rings that fit under the table
+constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
+constexpr uint32_t kCtrlOffset = kRingsAboveOffset + (kW - kRingsBelow) * kRingWords * 4;
+static_assert(kRingsBelow * kRingWords * 4 <= kTabOffset, "rings 0..5 must fit below the table");
+static_assert(kRingWords >= 2u * 32u * 31u, "a ring must hold two worst-case wide chunks");
 
 struct Ctrl {
-    unsigned long long bar_sums[kMaxSlots];     // workers -> publisher: chunk bit counts of tile k posted
-    unsigned long long bar_agg[kMaxSlots];      // publisher -> resolver: aggregate of tile k published
-    unsigned long long bar_prefix[kMaxSlots];   // resolver -> workers: global offset of tile k resolved
-    unsigned long long bar_emit[kMaxSlots];     // workers -> workers: chunk carries of tile k posted
-    unsigned long long bar_tile[4];             // publisher -> workers: ring[k & 3] holds the k-th tile id
-    unsigned long long ring[4];
-    unsigned long long sq[8];                   // the same sequence for the resolver (longer lived)
-    unsigned long long prefix[kMaxSlots];
-    uint32_t prev[kMaxSlots];
-    uint32_t flags[kMaxSlots];
-    uint32_t btile[kMaxSlots];
-    uint32_t woff[kMaxSlots][kW];
-    uint32_t sums[kMaxSlots][kW];
-    uint32_t carry_val[8][kW];
-    uint32_t carry_cnt[8][kW];
+    unsigned long long bar_sums[kDepth];        // workers -> publisher: chunk bit counts of tile k posted
+    unsigned long long bar_agg[kDepth];         // publisher -> resolver: aggregate of tile k published
+    unsigned long long bar_prefix[kDepth];      // resolver -> workers: global offset of tile k resolved
+    unsigned long long bar_emit[kDepth];        // workers -> workers: chunk carries of tile k posted
+    unsigned long long bar_tile[8];             // publisher -> workers: ring[k & 7] holds the k-th tile id
+    unsigned long long ring[8];
+    unsigned long long sq[16];                  // the same sequence for the resolvers (longer lived)
+    unsigned long long prefix[kDepth];
+    uint32_t prev[kDepth];
+    uint32_t flags[kDepth];
+    uint32_t btile[kDepth];
+    uint32_t woff[kDepth][kW];
+    uint32_t sums[kDepth][kW];
+    uint32_t carry_val[16][kW];
+    uint32_t carry_cnt[16][kW];
+    uint2 chunk[kW][kDepth];                    // worker-private: {ring offset, bits} of its staged chunks
 };
 
-// position k of a CTA's tile sequence -> staging slot k % NS and mbarrier parity (k / NS) & 1
-template <int NS>
-struct Cursor {
-    uint32_t k = 0, slot = 0, par = 0;
-    __device__ __forceinline__ void next()
-    {
-        k++;
-        if (++slot == (uint32_t)NS) {
-            slot = 0;
-            par ^= 1u;
-        }
-    }
-};
+// position k of a CTA's tile sequence -> slot k % kDepth and mbarrier parity (k / kDepth) & 1
+__device__ __forceinline__ uint32_t slot_of(uint32_t k) { return k & (uint32_t)(kDepth - 1); }
+__device__ __forceinline__ uint32_t par_of(uint32_t k) { return (k / (uint32_t)kDepth) & 1u; }
 
 // ---- small PTX helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
@@ -144,6 +129,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "r"(a), "r"(parity)
             : "memory");
     } while (!done);
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {
@@ -262,19 +259,18 @@ __device__ uint32_t bits_before(const EncParams &p, uint32_t tab_s, unsigned lon
 }
 
 // ---- publisher warp: tickets and tile aggregates ---------------------------------------------------------
-// Never waits on another CTA: as soon as the 16 chunk counts of a tile are in, their sum is published,
-// whatever state this CTA's own look-backs are in.
-template <bool WIDE>
+// Never waits on another CTA: as soon as the 16 chunk counts of a tile are in, their sum goes into the
+// tree, whatever state this CTA's own look-backs are in.
 __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
 {
-    constexpr int NS = Geo<WIDE>::NS;
     bool ended = false;
     auto draw = [&]() -> unsigned long long {            // raw ticket; its latency is hidden until first use
         unsigned long long tk = 0;
         if (lane == 0 && !ended) tk = atomicAdd(p.ticket, 1ULL);
         return tk;
     };
-    // k-th tile of this CTA: ring[k & 3] for the workers, sq[k & 7] for the resolver
+    // k-th tile of this CTA: ring[k & 7] for the workers, sq[k & 15] for the resolvers.  Tickets run
+    // kAhead positions ahead of the slowest worker, so a fast worker is not held up by a slow one.
     auto post = [&](uint32_t k, unsigned long long raw) -> unsigned long long {
         unsigned long long t = kNoTile;
         if (!ended) {
@@ -285,25 +281,31 @@ __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
             }
         }
         if (lane == 0) {
-            ctrl->ring[k & 3u] = t;
-            ctrl->sq[k & 7u] = t;
-            mbar_arrive(&ctrl->bar_tile[k & 3u]);
+            ctrl->ring[k & 7u] = t;
+            ctrl->sq[k & 15u] = t;
+            mbar_arrive(&ctrl->bar_tile[k & 7u]);
         }
         return t;
     };
 
-    unsigned long long t_cur = post(0, draw());
-    unsigned long long t_next = post(1, draw());
-    for (Cursor<NS> c;; c.next()) {
+    for (uint32_t j = 0; j < (uint32_t)kAhead; j++) post(j, draw());
+    __syncwarp();
+    for (uint32_t k = 0;; k++) {
+        const uint32_t slot = slot_of(k);
+        const unsigned long long t_cur = ctrl->sq[k & 15u];
         if (t_cur == kNoTile) {
-            if (lane == 0) mbar_arrive(&ctrl->bar_agg[c.slot]);      // wakes the resolver, which then stops too
+            // wake both resolvers (positions k and k + 1), which then stop too
+            if (lane == 0) {
+                mbar_arrive(&ctrl->bar_agg[slot]);
+                mbar_arrive(&ctrl->bar_agg[slot_of(k + 1u)]);
+            }
             break;
         }
-        const unsigned long long raw = draw();                       // position k + 2
-        mbar_wait(&ctrl->bar_sums[c.slot], c.par);
+        const unsigned long long raw = draw();                       // position k + kAhead
+        mbar_wait(&ctrl->bar_sums[slot], par_of(k));
 
         // exclusive scan of the 16 chunk bit counts
-        const uint32_t n = (lane < (uint32_t)kW) ? ctrl->sums[c.slot][lane] : 0u;
+        const uint32_t n = (lane < (uint32_t)kW) ? ctrl->sums[slot][lane] : 0u;
         uint32_t incl = n;
 #pragma unroll
         for (int d = 1; d < kW; d <<= 1) {
@@ -311,7 +313,7 @@ __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
             if (lane >= (uint32_t)d) incl += v;
         }
         const uint32_t btile = __shfl_sync(0xFFFFFFFFu, incl, kW - 1);
-        if (lane < (uint32_t)kW) ctrl->woff[c.slot][lane] = incl - n;
+        if (lane < (uint32_t)kW) ctrl->woff[slot][lane] = incl - n;
         // Fenwick update: lane j adds {1 tile, btile bits} to the j-th node above tile t_cur (1-based index
         // t_cur + 1, then repeatedly + lowbit).  Nodes at or beyond the last tile are never read: skip them.
         {
@@ -319,23 +321,22 @@ __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
             for (uint32_t j = 0; j < lane && i < p.n_tiles; j++) i += i & (0ULL - i);
             if (i < p.n_tiles) red_add_u64(&p.tree[i], kTreeOne | (unsigned long long)btile);
         }
+        // every worker is past pass 1 of tile k, so ring[(k + kAhead) & 7] (tile k + kAhead - 8) is dead
+        post(k + (uint32_t)kAhead, raw);
         __syncwarp();
         if (lane == 0) {
-            ctrl->btile[c.slot] = btile;
-            mbar_arrive(&ctrl->bar_agg[c.slot]);
+            ctrl->btile[slot] = btile;
+            mbar_arrive(&ctrl->bar_agg[slot]);
         }
-        // every worker is past pass 1 of tile k, so ring[(k + 2) & 3] (tile k - 2) is dead
-        t_cur = t_next;
-        t_next = post(c.k + 2u, raw);
     }
 }
 
 // ---- resolver warp: look-back over the Fenwick tree --------------------------------------------------------
+// Two resolver warps share the CTA's tile sequence: resolver r takes positions r, r + 2, r + 4, ...
 template <bool WIDE>
-__device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t lane)
+__device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t lane, uint32_t first)
 {
-    constexpr int NS = Geo<WIDE>::NS;
-    Prof prof(p, true);
+    Prof prof(p, first == 0);
     const long long t_all = prof.now();
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     // the symbol `lane + 1` places before a tile, for the (< 32) stream bits that precede it
@@ -346,13 +347,16 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
     };
 
     uint32_t sym = 0;
-    for (Cursor<NS> c;; c.next()) {
+    for (uint32_t k = first;; k += 2u) {
+        const uint32_t slot = slot_of(k);
         long long t0 = prof.now();
-        mbar_wait(&ctrl->bar_agg[c.slot], c.par);
+        mbar_wait(&ctrl->bar_agg[slot], par_of(k));
         prof.add(kProfWaitAgg, t0);
-        const unsigned long long tile = ctrl->sq[c.k & 7u];
+        const unsigned long long tile = ctrl->sq[k & 15u];
         if (tile == kNoTile) break;
-        if (c.k == 0) sym = tail_symbol(tile);
+        if (k == first) sym = tail_symbol(tile);
+        // this warp's next tile: its tail symbols have two tiles to land (sq[k + 2] is posted before agg[k - 2])
+        const uint32_t sym_next = tail_symbol(ctrl->sq[(k + 2u) & 15u]);
         prof.v[kProfTiles]++;
 
         // ---------------- look-back: the <= log2(n) tree nodes that tile the prefix [0, tile) ----------------
@@ -379,7 +383,7 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
             excl = p.start_bit + v;
         }
-        if (tile == p.end_tile - 1 && lane == 0) p.result->bits_end = excl + ctrl->btile[c.slot];
+        if (tile == p.end_tile - 1 && lane == 0) p.result->bits_end = excl + ctrl->btile[slot];
         prof.add(kProfLookback, t0);
 
         // ---------------- the (excl & 31) stream bits just before the tile ----------------
@@ -407,13 +411,12 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
             if (have < sh && first_sym > 32ULL) prev = bits_before<WIDE>(p, tab_s, first_sym, sh, lane);
         }
         if (lane == 0) {
-            ctrl->prefix[c.slot] = excl;
-            ctrl->prev[c.slot] = prev;
-            ctrl->flags[c.slot] = (tile == p.n_tiles - 1) ? 1u : 0u;
-            mbar_arrive(&ctrl->bar_prefix[c.slot]);
+            ctrl->prefix[slot] = excl;
+            ctrl->prev[slot] = prev;
+            ctrl->flags[slot] = (tile == p.n_tiles - 1) ? 1u : 0u;
+            mbar_arrive(&ctrl->bar_prefix[slot]);
         }
-        // the next tile's tail symbols: the load has a whole tile to land (sq[k+1] was posted before agg[k])
-        sym = tail_symbol(ctrl->sq[(c.k + 1u) & 7u]);
+        sym = sym_next;
         prof.add(kProfBitsBefore, t0);
     }
     prof.add(kProfResolver, t_all);
@@ -421,31 +424,24 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
 }
 
 // ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
-template <int NS>
-__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *st,
-                                         const Cursor<NS> &c, uint32_t n, uint32_t warp, uint32_t lane,
-                                         Prof &prof)
+__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *st, uint32_t k,
+                                         uint32_t n, uint32_t warp, uint32_t lane)
 {
-    long long t0 = prof.now();
-    mbar_wait(&ctrl->bar_emit[c.slot], c.par);
-    mbar_wait(&ctrl->bar_prefix[c.slot], c.par);
-    prof.add(kProfWaitPrefix, t0);
-    t0 = prof.now();
-
+    const uint32_t slot = slot_of(k);
     // the (< 32) bits that precede this chunk: neighbours' carries, then the tile's `prev`
     uint32_t cin = 0, have = 0;
     for (int r = (int)warp - 1; r >= 0 && have < 31u; r--) {
-        cin |= ctrl->carry_val[c.k & 7u][r] << have;
-        have += ctrl->carry_cnt[c.k & 7u][r];
+        cin |= ctrl->carry_val[k & 15u][r] << have;
+        have += ctrl->carry_cnt[k & 15u][r];
     }
-    if (have < 31u) cin |= ctrl->prev[c.slot] << have;
+    if (have < 31u) cin |= ctrl->prev[slot] << have;
 
-    const unsigned long long B = ctrl->prefix[c.slot] + ctrl->woff[c.slot][warp];
+    const unsigned long long B = ctrl->prefix[slot] + ctrl->woff[slot][warp];
     const uint32_t sh = (uint32_t)(B & 31ULL);
     const unsigned long long g0 = B >> 5;
     const unsigned long long end = B + n;
     const uint32_t nfull = (uint32_t)((end >> 5) - g0);        // words whose last bit is ours (<= ceil(n/32))
-    const bool last = ctrl->flags[c.slot] && warp == (uint32_t)kW - 1;   // the job's final word(s)
+    const bool last = ctrl->flags[slot] && warp == (uint32_t)kW - 1;   // the job's final word(s)
     if (!last && g0 + nfull <= p.out_cap_words) {
         // common case: every word this chunk owns comes from two neighbouring staged words
         uint32_t *out = p.out + g0;
@@ -469,26 +465,19 @@ __device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const u
         }
         if (spill) p.result->overflow = 1ULL;
     }
-    prof.add(kProfCopy, t0);
 }
 
 // ---- worker warp ----------------------------------------------------------------------------------------
 template <int G, bool WIDE, bool CHECK>
-__device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_base, Ctrl *ctrl, uint32_t warp,
+__device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl *ctrl, uint32_t warp,
                        uint32_t lane)
 {
-    constexpr int NS = Geo<WIDE>::NS;
-    constexpr int LAG = NS - 1;                               // copy-out trails the encode by LAG tiles
     constexpr int NG = (S + G - 1) / G;
-    constexpr int RW = Geo<WIDE>::kRegionWords;
     // byte 0 = lane*4, bytes 1..2 = bytes 2..3 of the table's window address (prmt source b)
     const uint32_t laneoff = lane * 4u | ((tab_s >> 16) << 8);
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     const unsigned long long n_bytes = p.n_words * 4ULL;
 
-    auto region = [&](uint32_t slot) {
-        return reinterpret_cast<uint32_t *>(smem_base + Geo<WIDE>::slot_offset(slot)) + warp * RW;
-    };
     auto chunk_word0 = [&](unsigned long long t) {
         return t * (unsigned long long)kTileWords + warp * (unsigned long long)(kChunkBytes / 4);
     };
@@ -498,17 +487,65 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_b
 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
+
+    // ---- the staging ring: chunks [retired, emitted) of this worker live in ring order from `tail` to `head`
+    uint32_t emitted = 0, retired = 0, head = 0, tail = 0;
+    auto retire = [&](bool blocking) {
+        const uint32_t k = retired, slot = slot_of(k);
+        if (blocking) {
+            const long long t0 = prof.now();
+            mbar_wait(&ctrl->bar_emit[slot], par_of(k));
+            mbar_wait(&ctrl->bar_prefix[slot], par_of(k));
+            prof.add(kProfWaitPrefix, t0);
+        }
+        const long long t0 = prof.now();
+        const uint2 ch = ctrl->chunk[warp][slot];
+        copy_out(p, ctrl, ring + ch.x, k, ch.y, warp, lane);
+        retired++;
+        if (retired < emitted)
+            tail = ctrl->chunk[warp][slot_of(retired)].x;
+        else
+            head = tail = 0;
+        __syncwarp();
+        prof.add(kProfCopy, t0);
+    };
+    auto try_alloc = [&](uint32_t need, uint32_t &start) -> bool {
+        if (emitted == retired) {
+            start = 0;
+            tail = 0;
+            head = need;
+            return true;
+        }
+        if (tail < head) {
+            if (head + need <= kRingWords) {
+                start = head;
+                head += need;
+                return true;
+            }
+            if (need <= tail) {                               // wrap; [head, end) stays unused until retired
+                start = 0;
+                head = need;
+                return true;
+            }
+            return false;
+        }
+        if (tail > head && head + need <= tail) {
+            start = head;
+            head += need;
+            return true;
+        }
+        return false;                                         // tail == head with chunks in flight: full
+    };
+
     uint32_t w[8], wn[8];
     mbar_wait(&ctrl->bar_tile[0], 0);
     unsigned long long tile = ctrl->ring[0];
     if (tile != kNoTile && chunk_full(tile)) ld_stream_v8(p.in + chunk_word0(tile) + lane * 8u, w);
 
-    uint32_t n_hist[LAG];                                     // bit counts of the tiles awaiting copy-out
-#pragma unroll
-    for (int i = 0; i < LAG; i++) n_hist[i] = 0;
-    Cursor<NS> c, cc;                                         // encode position, copy-out position
-    for (; tile != kNoTile; c.next()) {
-        uint32_t *st = region(c.slot);
+    for (; tile != kNoTile;) {
+        const uint32_t k = emitted, slot = slot_of(k);
+        // slot k % kDepth still belongs to tile k - kDepth until that one has been copied out
+        if (emitted - retired >= (uint32_t)kDepth) retire(true);
 
         // ---------------- prefetch the next tile's chunk ----------------
         // Scoreboard slots count per instruction, not per register: the load below and the one that filled
@@ -517,10 +554,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_b
 #pragma unroll
         for (int i = 0; i < 8; i++) asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
         long long t0 = prof.now();
-        mbar_wait(&ctrl->bar_tile[(c.k + 1u) & 3u], ((c.k + 1u) >> 2) & 1u);
+        mbar_wait(&ctrl->bar_tile[(k + 1u) & 7u], ((k + 1u) >> 3) & 1u);
         prof.add(kProfWaitTile, t0);
         t0 = prof.now();
-        const unsigned long long tnext = ctrl->ring[(c.k + 1u) & 3u];
+        const unsigned long long tnext = ctrl->ring[(k + 1u) & 7u];
         if (tnext != kNoTile && chunk_full(tnext)) ld_stream_v8(p.in + chunk_word0(tnext) + lane * 8u, wn);
 
         // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
@@ -578,11 +615,17 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_b
         const uint32_t q0 = incl - bt;
         const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
         if (lane == 31) {
-            ctrl->sums[c.slot][warp] = n;
-            mbar_arrive(&ctrl->bar_sums[c.slot]);
+            ctrl->sums[slot][warp] = n;
+            mbar_arrive(&ctrl->bar_sums[slot]);
         }
 
-        // ---------------- pass 2: bits -> this warp's staging region (chunk-relative alignment) ----------------
+        // ---------------- room in the ring (older chunks leave first if it is full) ----------------
+        const uint32_t need = n ? ((n + 31u) >> 5) : 1u;
+        uint32_t start = 0;
+        while (!try_alloc(need, start)) retire(true);
+        uint32_t *st = ring + start;
+
+        // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
         // fast path: a staging word has at most two owners (needs >= 32 bits from every lane) and
         // every group fits the 32-bit window
         const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u && (!CHECK || (ormask & ~31u) == 0u));
@@ -603,10 +646,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_b
                 lo_prev = los[g];
             }
             const uint32_t f = q & 31u;
-            const uint32_t tail = f ? (lo_prev << (32u - f)) : 0u;
-            const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tail, 1);
+            const uint32_t tailw = f ? (lo_prev << (32u - f)) : 0u;
+            const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
             if (lane != 0 && (q0 & 31u)) st[q0 >> 5] |= left_tail;   // my head word, completed by me
-            if (lane == 31 && f) st[n >> 5] = tail;
+            if (lane == 31 && f) st[n >> 5] = tailw;
         } else {
             for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) st[j] = 0u;
             __syncwarp();
@@ -639,34 +682,25 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, unsigned char *smem_b
                 const uint32_t w1 = st[a], w0 = a ? st[a - 1u] : 0u;
                 val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
             }
-            ctrl->carry_val[c.k & 7u][warp] = val;
-            ctrl->carry_cnt[c.k & 7u][warp] = n < 31u ? n : 31u;
-            mbar_arrive(&ctrl->bar_emit[c.slot]);
+            ctrl->carry_val[k & 15u][warp] = val;
+            ctrl->carry_cnt[k & 15u][warp] = n < 31u ? n : 31u;
+            ctrl->chunk[warp][slot] = make_uint2(start, n);
+            mbar_arrive(&ctrl->bar_emit[slot]);
         }
+        emitted++;
+        __syncwarp();
         prof.add(kProfEmit, t0);
 
-        // ---------------- copy-out of tile k - LAG (its look-back had LAG tiles of slack) ----------------
-        if (c.k >= (uint32_t)LAG) {
-            copy_out<NS>(p, ctrl, region(cc.slot), cc, n_hist[LAG - 1], warp, lane, prof);
-            cc.next();
-        }
-#pragma unroll
-        for (int i = LAG - 1; i > 0; i--) n_hist[i] = n_hist[i - 1];
-        n_hist[0] = n;
+        // ---------------- copy out every chunk whose global offset is already known ----------------
+        while (retired < emitted && mbar_test(&ctrl->bar_prefix[slot_of(retired)], par_of(retired)) &&
+               mbar_test(&ctrl->bar_emit[slot_of(retired)], par_of(retired)))
+            retire(false);
 
-        __syncwarp();
         tile = tnext;
 #pragma unroll
         for (int i = 0; i < 8; i++) w[i] = wn[i];
     }
-    // drain: positions cc.k .. c.k-1 are still staged; the count of position c.k-1-i is n_hist[i]
-#pragma unroll
-    for (int i = LAG - 1; i >= 0; i--) {
-        if (c.k > (uint32_t)i && cc.k == c.k - 1u - (uint32_t)i) {
-            copy_out<NS>(p, ctrl, region(cc.slot), cc, n_hist[i], warp, lane, prof);
-            cc.next();
-        }
-    }
+    while (retired < emitted) retire(true);
     prof.add(kProfWorker, t_worker);
     prof.flush(p, lane);
 }
@@ -678,7 +712,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     extern __shared__ __align__(1024) uint32_t smem[];
     unsigned char *base = reinterpret_cast<unsigned char *>(smem);
     uint32_t *tab = reinterpret_cast<uint32_t *>(base + kTabOffset);
-    Ctrl *ctrl = reinterpret_cast<Ctrl *>(base + Geo<WIDE>::kCtrlOffset);
+    Ctrl *ctrl = reinterpret_cast<Ctrl *>(base + kCtrlOffset);
     const uint32_t tab_s = smem_addr(tab);
     if (tab_s & 0xFFFFu) {
         // the shared window is not laid out as assumed: refuse loudly instead of mis-encoding
@@ -696,29 +730,32 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
         p.tree_zero[i] = 0ULL;
     fill_table<WIDE>(tab, p.table, tid);
     if (tid == 0) {
-        for (int i = 0; i < kMaxSlots; i++) {
+        for (int i = 0; i < kDepth; i++) {
             mbar_init(&ctrl->bar_sums[i], kW);
             mbar_init(&ctrl->bar_emit[i], kW);
             mbar_init(&ctrl->bar_agg[i], 1);
             mbar_init(&ctrl->bar_prefix[i], 1);
         }
-        for (int i = 0; i < 4; i++) mbar_init(&ctrl->bar_tile[i], 1);
+        for (int i = 0; i < 8; i++) mbar_init(&ctrl->bar_tile[i], 1);
     }
     __syncthreads();
 
-    if (warp == (uint32_t)kPublisherWarp)
-        publisher<WIDE>(p, ctrl, lane);
-    else if (warp == (uint32_t)kResolverWarp)
-        resolver<WIDE>(p, tab_s, ctrl, lane);
-
-    else
-        worker<G, WIDE, CHECK>(p, tab_s, base, ctrl, warp, lane);
+    if (warp < (uint32_t)kW) {
+        uint32_t *ring = warp < (uint32_t)kRingsBelow
+                             ? smem + warp * kRingWords
+                             : reinterpret_cast<uint32_t *>(base + kRingsAboveOffset) + (warp - kRingsBelow) * kRingWords;
+        worker<G, WIDE, CHECK>(p, tab_s, ring, ctrl, warp, lane);
+    } else if (warp == (uint32_t)kPublisherWarp) {
+        publisher(p, ctrl, lane);
+    } else {
+        resolver<WIDE>(p, tab_s, ctrl, lane, warp - (uint32_t)kResolverWarp);
+    }
 }
 
 template <bool WIDE>
 constexpr size_t smem_bytes()
 {
-    return (size_t)Geo<WIDE>::kCtrlOffset + sizeof(Ctrl);
+    return (size_t)kCtrlOffset + sizeof(Ctrl);
 }
 
 // ---- variant table ------------------------------------------------------------------------------------

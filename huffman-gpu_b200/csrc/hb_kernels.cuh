@@ -10,10 +10,10 @@
 namespace hb {
 
 // ---- geometry of the single-pass encoder ---------------------------------------------------------
-// One persistent CTA per SM: kEncWorkers worker warps + a publisher warp + a resolver warp.  A tile is the CTA's unit of
+// One persistent CTA per SM: kEncWorkers worker warps + a publisher warp + two resolver warps.  A tile is the CTA's unit of
 // work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
 constexpr int kEncWorkers = 16;
-constexpr int kEncThreads = (kEncWorkers + 2) * 32;
+constexpr int kEncThreads = (kEncWorkers + 3) * 32;
 constexpr int kSymPerThread = 32;                                     // symbols (bytes) per thread per tile
 constexpr int kChunkBytes = 32 * kSymPerThread;                       // one warp: 1 KiB
 constexpr int kTileBytes = kEncWorkers * kChunkBytes;                 // 16 KiB
