@@ -71,7 +71,7 @@ constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 //   [rings of workers 0..5 | pad] up to the boundary, [table 64 KiB], [rings of workers 6..15], [control].
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
 constexpr uint32_t kTabOffset = 65536 - kSmemReserved;  // table offset inside the dynamic block
-constexpr int kAhead = 4;                               // tile tickets drawn ahead of the slowest worker
+constexpr int kAhead = 3;                               // tile tickets drawn ahead of the slowest worker
 constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
 constexpr uint32_t kRingWords = 2432;                   // per worker; >= 3 worst-case packed chunks (3 * 768)
 constexpr int kRingsBelow = 6;                          // rings that fit under the table
@@ -119,8 +119,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
 {
     const uint32_t a = smem_addr(bar);
-    uint32_t done;
-    do {
+    for (;;) {
+        uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -128,7 +128,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "=r"(done)
             : "r"(a), "r"(parity)
             : "memory");
-    } while (!done);
+        if (done) break;
+        __nanosleep(64);                // a blocked warp must not compete for issue slots
+    }
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity)
 {
@@ -160,9 +162,10 @@ __device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t (&w)[8]
                    "=r"(w[7])
                  : "l"(p));
 }
-// ---- optional cycle accounting ($HB_PROFILE=1; one branch per tile when off) ----------------------------
+// ---- optional cycle accounting: build with -DHB_PROFILE and run with $HB_PROFILE=1 --------------------
 enum { kProfWaitTile = 0, kProfWaitPrefix, kProfWorker, kProfWaitSums, kProfWaitAgg, kProfLookback,
        kProfBitsBefore, kProfResolver, kProfTiles, kProfPolls, kProfPass1, kProfEmit, kProfCopy, kProfCount };
+#ifdef HB_PROFILE
 struct Prof {
     unsigned long long v[kProfCount];
     bool on;
@@ -172,6 +175,7 @@ struct Prof {
     }
     __device__ __forceinline__ long long now() const { return on ? clock64() : 0; }
     __device__ __forceinline__ void add(int i, long long t0) { if (on) v[i] += (unsigned long long)(clock64() - t0); }
+    __device__ __forceinline__ void count(int i) { v[i]++; }
     __device__ void flush(const EncParams &p, uint32_t lane)
     {
         if (on && lane == 0)
@@ -179,6 +183,15 @@ struct Prof {
                 if (v[i]) atomicAdd(&p.prof[i], v[i]);
     }
 };
+#else
+struct Prof {
+    __device__ Prof(const EncParams &, bool) {}
+    __device__ __forceinline__ long long now() const { return 0; }
+    __device__ __forceinline__ void add(int, long long) {}
+    __device__ __forceinline__ void count(int) {}
+    __device__ __forceinline__ void flush(const EncParams &, uint32_t) {}
+};
+#endif
 
 // ---- codebook in shared memory ---------------------------------------------------------------------
 // slot(sym) = 256 bytes: words 0..31 = the entry replicated per lane; wide tables keep the length in
@@ -357,7 +370,7 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
         if (k == first) sym = tail_symbol(tile);
         // this warp's next tile: its tail symbols have two tiles to land (sq[k + 2] is posted before agg[k - 2])
         const uint32_t sym_next = tail_symbol(ctrl->sq[(k + 2u) & 15u]);
-        prof.v[kProfTiles]++;
+        prof.count(kProfTiles);
 
         // ---------------- look-back: the <= log2(n) tree nodes that tile the prefix [0, tile) ----------------
         // lane j owns node i_j (i_0 = tile, i_{j+1} = i_j - lowbit(i_j)), final once it has counted lowbit(i_j) tiles
@@ -374,9 +387,9 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
                     v = ld_relaxed_u64(&p.tree[i]);
                     pending = (v & ~kTreeSumMask) != want;
                 }
-                prof.v[kProfPolls]++;
+                prof.count(kProfPolls);
                 if (!__any_sync(0xFFFFFFFFu, pending)) break;
-                __nanosleep(64);
+                __nanosleep(200);
             }
             v &= kTreeSumMask;
 #pragma unroll
@@ -478,13 +491,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     const unsigned long long n_bytes = p.n_words * 4ULL;
 
-    auto chunk_word0 = [&](unsigned long long t) {
-        return t * (unsigned long long)kTileWords + warp * (unsigned long long)(kChunkBytes / 4);
-    };
-    auto chunk_full = [&](unsigned long long t) {
-        return chunk_word0(t) + (unsigned long long)(kChunkBytes / 4) <= p.n_words;
-    };
-
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
 
@@ -492,10 +498,12 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
     uint32_t emitted = 0, retired = 0, head = 0, tail = 0;
     auto retire = [&](bool blocking) {
         const uint32_t k = retired, slot = slot_of(k);
-        if (blocking) {
+        {
+            // the offset needs every worker's count (pass 1), the carries every worker's bits (pass 2): the
+            // second is almost always in by the time the first has been through the look-back
             const long long t0 = prof.now();
+            if (blocking) mbar_wait(&ctrl->bar_prefix[slot], par_of(k));
             mbar_wait(&ctrl->bar_emit[slot], par_of(k));
-            mbar_wait(&ctrl->bar_prefix[slot], par_of(k));
             prof.add(kProfWaitPrefix, t0);
         }
         const long long t0 = prof.now();
@@ -537,10 +545,20 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         return false;                                         // tail == head with chunks in flight: full
     };
 
+    // this warp's chunk of tile t starts at word t * kTileWords + warp_word0; it is `full` when it lies
+    // entirely inside the input
+    const uint32_t warp_word0 = warp * (uint32_t)(kChunkBytes / 4);
+    const uint32_t *in_lane = p.in + warp_word0 + lane * 8u;
+    const unsigned long long full_tiles =                       // tiles whose chunk for this warp is full
+        p.n_words >= warp_word0 + (uint32_t)(kChunkBytes / 4)
+            ? (p.n_words - warp_word0 - (uint32_t)(kChunkBytes / 4)) / (unsigned long long)kTileWords + 1ULL
+            : 0ULL;
+
     uint32_t w[8], wn[8];
     mbar_wait(&ctrl->bar_tile[0], 0);
     unsigned long long tile = ctrl->ring[0];
-    if (tile != kNoTile && chunk_full(tile)) ld_stream_v8(p.in + chunk_word0(tile) + lane * 8u, w);
+    bool full = tile < full_tiles;                            // kNoTile is never < full_tiles
+    if (full) ld_stream_v8(in_lane + tile * (unsigned long long)kTileWords, w);
 
     for (; tile != kNoTile;) {
         const uint32_t k = emitted, slot = slot_of(k);
@@ -558,12 +576,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         prof.add(kProfWaitTile, t0);
         t0 = prof.now();
         const unsigned long long tnext = ctrl->ring[(k + 1u) & 7u];
-        if (tnext != kNoTile && chunk_full(tnext)) ld_stream_v8(p.in + chunk_word0(tnext) + lane * 8u, wn);
+        const bool full_next = tnext < full_tiles;
+        if (full_next) ld_stream_v8(in_lane + tnext * (unsigned long long)kTileWords, wn);
 
         // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
-        const bool full = chunk_full(tile);                   // warp-uniform
-        const unsigned long long sym0 =
-            tile * (unsigned long long)kTileBytes + warp * (unsigned long long)kChunkBytes + lane * (unsigned long long)S;
         uint32_t los[NG], gss[NG];
         uint32_t bt = 0, ormask = 0;
         if (full) {
@@ -591,6 +607,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
                 }
             }
         } else {
+            const unsigned long long sym0 = tile * (unsigned long long)kTileBytes + warp * (uint32_t)kChunkBytes + lane * (uint32_t)S;
 #pragma unroll 1
             for (int i = 0; i < S; i++) {
                 if (sym0 + i < n_bytes) {
@@ -630,27 +647,28 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         // every group fits the 32-bit window
         const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u && (!CHECK || (ormask & ~31u) == 0u));
         if (fast) {
-            uint32_t q = q0;
-            uint32_t *wp = st + (q0 >> 5);                    // the word this lane completes next
+            uint32_t r = q0 & 31u;                            // bits already in the word being filled
+            uint32_t *wp = st + (q0 >> 5);                    // that word
             uint32_t lo_prev = 0;
 #pragma unroll
             for (int g = 0; g < NG; g++) {
-                const uint32_t qn = q + gss[g];
-                if ((qn ^ q) & ~31u) {
-                    // the 32 bits that end at the boundary: low (qn & 31) of them come from the window
-                    // before this group, the rest from the window after it
+                r += gss[g];
+                if (r >= 32u) {
+                    // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
+                    // before this group, the rest from the window after it (funnel shifts use r mod 32)
                     const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                    *wp++ = __funnelshift_r(los[g], hi, qn);
+                    *wp++ = __funnelshift_r(los[g], hi, r);
+                    r -= 32u;
                 }
-                q = qn;
                 lo_prev = los[g];
             }
-            const uint32_t f = q & 31u;
+            const uint32_t f = r;
             const uint32_t tailw = f ? (lo_prev << (32u - f)) : 0u;
             const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
             if (lane != 0 && (q0 & 31u)) st[q0 >> 5] |= left_tail;   // my head word, completed by me
             if (lane == 31 && f) st[n >> 5] = tailw;
         } else {
+            const unsigned long long sym0 = tile * (unsigned long long)kTileBytes + warp * (uint32_t)kChunkBytes + lane * (uint32_t)S;
             for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) st[j] = 0u;
             __syncwarp();
             uint32_t q = q0, lo = 0;
@@ -692,11 +710,11 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         prof.add(kProfEmit, t0);
 
         // ---------------- copy out every chunk whose global offset is already known ----------------
-        while (retired < emitted && mbar_test(&ctrl->bar_prefix[slot_of(retired)], par_of(retired)) &&
-               mbar_test(&ctrl->bar_emit[slot_of(retired)], par_of(retired)))
+        while (retired < emitted && mbar_test(&ctrl->bar_prefix[slot_of(retired)], par_of(retired)))
             retire(false);
 
         tile = tnext;
+        full = full_next;
 #pragma unroll
         for (int i = 0; i < 8; i++) w[i] = wn[i];
     }
