@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libhuffb200.so")
 HB_OK = 0
 HB_ERR_ARG, HB_ERR_CAPACITY, HB_ERR_CODELEN, HB_ERR_CODEWORD = -1, -2, -3, -4
 HB_ERR_CUDA, HB_ERR_NOMEM, HB_ERR_STATE = -5, -6, -7
-TILE_BYTES = 16384
+TILE_BYTES = 32768          # hb::kTileBytes (csrc/hb_kernels.cuh)
 
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)

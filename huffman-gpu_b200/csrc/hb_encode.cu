@@ -54,7 +54,8 @@ namespace hb {
 namespace {
 
 constexpr int kW = kEncWorkers;
-constexpr int S = kSymPerThread;
+constexpr int S = kSymPerThread;                        // symbols per lane per sub-block
+constexpr int kSub = kSubBlocks;
 constexpr int kPublisherWarp = kW;
 constexpr int kResolverWarp = kW + 1;
 constexpr int kSlotStride = 256;                        // table stride per symbol (bytes)
@@ -73,12 +74,14 @@ constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSh
 constexpr uint32_t kTabOffset = 65536 - kSmemReserved;  // table offset inside the dynamic block
 constexpr int kAhead = 3;                               // tile tickets drawn ahead of the slowest worker
 constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
-constexpr uint32_t kRingWords = 2432;                   // per worker; >= 3 worst-case packed chunks (3 * 768)
-constexpr int kRingsBelow = 6;                          // rings that fit under the table
+constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
+constexpr uint32_t kRingMask = kRingWords - 1;
+constexpr int kRingsBelow = 7;                          // rings that fit under the table
 constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
 constexpr uint32_t kCtrlOffset = kRingsAboveOffset + (kW - kRingsBelow) * kRingWords * 4;
-static_assert(kRingsBelow * kRingWords * 4 <= kTabOffset, "rings 0..5 must fit below the table");
-static_assert(kRingWords >= 2u * 32u * 31u, "a ring must hold two worst-case wide chunks");
+static_assert(kRingsBelow * kRingWords * 4 <= kTabOffset, "rings 0..6 must fit below the table");
+// a chunk is staged contiguously (mod ring size) and must fit even when every symbol takes the longest code
+static_assert((uint32_t)kSubBlocks * S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
 
 struct Ctrl {
     unsigned long long bar_sums[kDepth];        // workers -> publisher: chunk bit counts of tile k posted
@@ -96,7 +99,7 @@ struct Ctrl {
     uint32_t sums[kDepth][kW];
     uint32_t carry_val[16][kW];
     uint32_t carry_cnt[16][kW];
-    uint2 chunk[kW][kDepth];                    // worker-private: {ring offset, bits} of its staged chunks
+    uint2 chunk[kW][kDepth];                    // worker-private: {ring position, bits} of its staged chunks
 };
 
 // position k of a CTA's tile sequence -> slot k % kDepth and mbarrier parity (k / kDepth) & 1
@@ -437,8 +440,9 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
 }
 
 // ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
-__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *st, uint32_t k,
-                                         uint32_t n, uint32_t warp, uint32_t lane)
+// The chunk occupies ring words start, start+1, ... (mod kRingWords).
+__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *ring, uint32_t start,
+                                         uint32_t k, uint32_t n, uint32_t warp, uint32_t lane)
 {
     const uint32_t slot = slot_of(k);
     // the (< 32) bits that precede this chunk: neighbours' carries, then the tile's `prev`
@@ -460,16 +464,16 @@ __device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const u
         uint32_t *out = p.out + g0;
 #pragma unroll 2
         for (uint32_t j = lane; j < nfull; j += 32u) {
-            const uint32_t before = j ? st[j - 1u] : cin;
-            out[j] = __funnelshift_r(st[j], before, sh);
+            const uint32_t before = j ? ring[(start + j - 1u) & kRingMask] : cin;
+            out[j] = __funnelshift_r(ring[(start + j) & kRingMask], before, sh);
         }
     } else {
         const uint32_t nwrite = nfull + (last ? 1u : 0u);
         const uint32_t nstage = (n + 31u) >> 5;
         bool spill = false;
         for (uint32_t j = lane; j < nwrite; j += 32u) {
-            const uint32_t cur = (j < nstage) ? st[j] : 0u;
-            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? st[j - 1] : 0u);
+            const uint32_t cur = (j < nstage) ? ring[(start + j) & kRingMask] : 0u;
+            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? ring[(start + j - 1u) & kRingMask] : 0u);
             const uint32_t v = __funnelshift_r(cur, before, sh);
             if (g0 + j < p.out_cap_words)
                 p.out[g0 + j] = v;
@@ -486,6 +490,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
                        uint32_t lane)
 {
     constexpr int NG = (S + G - 1) / G;
+    constexpr uint32_t kWorst = (uint32_t)S * (WIDE ? 31u : 24u);   // words one sub-block can emit at most
     // byte 0 = lane*4, bytes 1..2 = bytes 2..3 of the table's window address (prmt source b)
     const uint32_t laneoff = lane * 4u | ((tab_s >> 16) << 8);
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
@@ -494,7 +499,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
 
-    // ---- the staging ring: chunks [retired, emitted) of this worker live in ring order from `tail` to `head`
+    // ---- the staging ring: chunks [retired, emitted) of this worker, then the chunk being encoded, occupy ring
+    //      positions [tail, head + words so far); positions are absolute counters, the index is position mod size
     uint32_t emitted = 0, retired = 0, head = 0, tail = 0;
     auto retire = [&](bool blocking) {
         const uint32_t k = retired, slot = slot_of(k);
@@ -508,215 +514,200 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         }
         const long long t0 = prof.now();
         const uint2 ch = ctrl->chunk[warp][slot];
-        copy_out(p, ctrl, ring + ch.x, k, ch.y, warp, lane);
+        copy_out(p, ctrl, ring, ch.x, k, ch.y, warp, lane);
         retired++;
-        if (retired < emitted)
-            tail = ctrl->chunk[warp][slot_of(retired)].x;
-        else
-            head = tail = 0;
+        tail = (retired < emitted) ? ctrl->chunk[warp][slot_of(retired)].x : head;
         __syncwarp();
         prof.add(kProfCopy, t0);
     };
-    auto try_alloc = [&](uint32_t need, uint32_t &start) -> bool {
-        if (emitted == retired) {
-            start = 0;
-            tail = 0;
-            head = need;
-            return true;
-        }
-        if (tail < head) {
-            if (head + need <= kRingWords) {
-                start = head;
-                head += need;
-                return true;
-            }
-            if (need <= tail) {                               // wrap; [head, end) stays unused until retired
-                start = 0;
-                head = need;
-                return true;
-            }
-            return false;
-        }
-        if (tail > head && head + need <= tail) {
-            start = head;
-            head += need;
-            return true;
-        }
-        return false;                                         // tail == head with chunks in flight: full
-    };
 
-    // this warp's chunk of tile t starts at word t * kTileWords + warp_word0; it is `full` when it lies
-    // entirely inside the input
-    const uint32_t warp_word0 = warp * (uint32_t)(kChunkBytes / 4);
-    const uint32_t *in_lane = p.in + warp_word0 + lane * 8u;
-    const unsigned long long full_tiles =                       // tiles whose chunk for this warp is full
-        p.n_words >= warp_word0 + (uint32_t)(kChunkBytes / 4)
-            ? (p.n_words - warp_word0 - (uint32_t)(kChunkBytes / 4)) / (unsigned long long)kTileWords + 1ULL
-            : 0ULL;
+    // sub-block j (0 .. kSub-1) of this warp's chunk of tile t starts at word (t * kSub * kW + warp * kSub + j) * 256;
+    // a sub-block is `full` when it lies entirely inside the input
+    const unsigned long long full_subs = p.n_words / 256ULL;     // global sub-block indices below this are full
+    const uint32_t *in_lane = p.in + lane * 8u;
+    auto sub_index = [&](unsigned long long t, uint32_t j) {
+        return (t * (unsigned long long)kW + warp) * (unsigned long long)kSub + j;
+    };
 
     uint32_t w[8], wn[8];
     mbar_wait(&ctrl->bar_tile[0], 0);
     unsigned long long tile = ctrl->ring[0];
-    bool full = tile < full_tiles;                            // kNoTile is never < full_tiles
-    if (full) ld_stream_v8(in_lane + tile * (unsigned long long)kTileWords, w);
+    bool full = tile != kNoTile && sub_index(tile, 0) < full_subs;
+    if (full) ld_stream_v8(in_lane + sub_index(tile, 0) * 256ULL, w);
 
     for (; tile != kNoTile;) {
         const uint32_t k = emitted, slot = slot_of(k);
         // slot k % kDepth still belongs to tile k - kDepth until that one has been copied out
         if (emitted - retired >= (uint32_t)kDepth) retire(true);
 
-        // ---------------- prefetch the next tile's chunk ----------------
-        // Scoreboard slots count per instruction, not per register: the load below and the one that filled
-        // `w` a tile ago are the same SASS instruction, so the first read of `w` would also wait for the
-        // NEW load.  Reading `w` here, before the new load is issued, only waits for the old one.
-#pragma unroll
-        for (int i = 0; i < 8; i++) asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
         long long t0 = prof.now();
         mbar_wait(&ctrl->bar_tile[(k + 1u) & 7u], ((k + 1u) >> 3) & 1u);
         prof.add(kProfWaitTile, t0);
-        t0 = prof.now();
         const unsigned long long tnext = ctrl->ring[(k + 1u) & 7u];
-        const bool full_next = tnext < full_tiles;
-        if (full_next) ld_stream_v8(in_lane + tnext * (unsigned long long)kTileWords, wn);
 
-        // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
-        uint32_t los[NG], gss[NG];
-        uint32_t bt = 0, ormask = 0;
-        if (full) {
-            uint32_t lo = 0, gs = 0;
-#pragma unroll
-            for (int i = 0; i < S; i++) {
-                // {lane*4, symbol, table address bytes 2..3}: the whole lookup address in one prmt
-                const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
-                if (WIDE) {
-                    const uint32_t cwl = tab_ld(off);
-                    const uint32_t l = tab_ld_len(off);
-                    lo = __funnelshift_l(cwl, lo, l);
-                    gs += l;
-                } else {
-                    const uint32_t e = tab_ld(off);
-                    lo = __funnelshift_l(e, lo, e);           // (lo << len) | cw, len = e & 31
-                    gs = __dp4a(e, 1u, gs);                   // + (e & 0xFF)
-                }
-                if ((i % G) == G - 1 || i == S - 1) {
-                    los[i / G] = lo;
-                    gss[i / G] = gs;
-                    bt += gs;
-                    if (CHECK) ormask |= gs;
-                    gs = 0;
-                }
-            }
-        } else {
-            const unsigned long long sym0 = tile * (unsigned long long)kTileBytes + warp * (uint32_t)kChunkBytes + lane * (uint32_t)S;
+        uint32_t qbase = 0;                                    // bits of this chunk emitted so far
+        uint32_t prev_tail = 0;                                // the partial word that ends at qbase (left-aligned)
 #pragma unroll 1
-            for (int i = 0; i < S; i++) {
-                if (sym0 + i < n_bytes) {
-                    uint32_t cwl, l;
-                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
-                    bt += l;
-                }
-            }
-#pragma unroll
-            for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
-        }
-        prof.add(kProfPass1, t0);
-        t0 = prof.now();
+        for (uint32_t sub = 0; sub < (uint32_t)kSub; sub++) {
+            // ---------------- room for one worst-case sub-block (older chunks leave first) ----------------
+            while (head + (qbase >> 5) + kWorst + 2u - tail > kRingWords) retire(true);
 
-        // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
-        uint32_t incl = bt;
+            // ---------------- prefetch the next sub-block ----------------
+            // Scoreboard slots count per instruction, not per register: the load below and the one that
+            // filled `w` a sub-block ago are the same SASS instruction, so the first read of `w` would also
+            // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old.
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
-        }
-        const uint32_t q0 = incl - bt;
-        const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        if (lane == 31) {
-            ctrl->sums[slot][warp] = n;
-            mbar_arrive(&ctrl->bar_sums[slot]);
-        }
+            for (int i = 0; i < 8; i++) asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
+            t0 = prof.now();
+            const bool last_sub = sub + 1u == (uint32_t)kSub;
+            const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
+            const bool full_next = (!last_sub || tnext != kNoTile) && nsub < full_subs;
+            if (full_next) ld_stream_v8(in_lane + nsub * 256ULL, wn);
 
-        // ---------------- room in the ring (older chunks leave first if it is full) ----------------
-        const uint32_t need = n ? ((n + 31u) >> 5) : 1u;
-        uint32_t start = 0;
-        while (!try_alloc(need, start)) retire(true);
-        uint32_t *st = ring + start;
-
-        // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
-        // fast path: a staging word has at most two owners (needs >= 32 bits from every lane) and
-        // every group fits the 32-bit window
-        const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u && (!CHECK || (ormask & ~31u) == 0u));
-        if (fast) {
-            uint32_t r = q0 & 31u;                            // bits already in the word being filled
-            uint32_t *wp = st + (q0 >> 5);                    // that word
-            uint32_t lo_prev = 0;
+            // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
+            const unsigned long long sym0 = sub_index(tile, sub) * 1024ULL + lane * (uint32_t)S;   // slow paths only
+            uint32_t los[NG], gss[NG];
+            uint32_t bt = 0, ormask = 0;
+            if (full) {
+                uint32_t lo = 0, gs = 0;
 #pragma unroll
-            for (int g = 0; g < NG; g++) {
-                r += gss[g];
-                if (r >= 32u) {
-                    // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
-                    // before this group, the rest from the window after it (funnel shifts use r mod 32)
-                    const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                    *wp++ = __funnelshift_r(los[g], hi, r);
-                    r -= 32u;
-                }
-                lo_prev = los[g];
-            }
-            const uint32_t f = r;
-            const uint32_t tailw = f ? (lo_prev << (32u - f)) : 0u;
-            const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
-            if (lane != 0 && (q0 & 31u)) st[q0 >> 5] |= left_tail;   // my head word, completed by me
-            if (lane == 31 && f) st[n >> 5] = tailw;
-        } else {
-            const unsigned long long sym0 = tile * (unsigned long long)kTileBytes + warp * (uint32_t)kChunkBytes + lane * (uint32_t)S;
-            for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) st[j] = 0u;
-            __syncwarp();
-            uint32_t q = q0, lo = 0;
-#pragma unroll 1
-            for (int i = 0; i < S; i++) {
-                if (sym0 + i < n_bytes) {
-                    uint32_t cwl, l;
-                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
-                    if (l) {
-                        const uint32_t ln = __funnelshift_l(cwl, lo, l);
-                        const uint32_t qn = q + l;
-                        if ((qn ^ q) & ~31u)
-                            atomicOr(&st[(qn >> 5) - 1u], __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
-                        q = qn;
-                        lo = ln;
+                for (int i = 0; i < S; i++) {
+                    // {lane*4, symbol, table address bytes 2..3}: the whole lookup address in one prmt
+                    const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
+                    if (WIDE) {
+                        const uint32_t cwl = tab_ld(off);
+                        const uint32_t l = tab_ld_len(off);
+                        lo = __funnelshift_l(cwl, lo, l);
+                        gs += l;
+                    } else {
+                        const uint32_t e = tab_ld(off);
+                        lo = __funnelshift_l(e, lo, e);       // (lo << len) | cw, len = e & 31
+                        gs = __dp4a(e, 1u, gs);               // + (e & 0xFF)
+                    }
+                    if ((i % G) == G - 1 || i == S - 1) {
+                        los[i / G] = lo;
+                        gss[i / G] = gs;
+                        bt += gs;
+                        if (CHECK) ormask |= gs;
+                        gs = 0;
                     }
                 }
+            } else {
+#pragma unroll 1
+                for (int i = 0; i < S; i++) {
+                    if (sym0 + i < n_bytes) {
+                        uint32_t cwl, l;
+                        fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
+                        bt += l;
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
             }
-            const uint32_t f = q & 31u;
-            if (f) atomicOr(&st[q >> 5], lo << (32u - f));
+            prof.add(kProfPass1, t0);
+            t0 = prof.now();
+
+            // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
+            uint32_t incl = bt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                if (lane >= (uint32_t)d) incl += v;
+            }
+            const uint32_t q0 = qbase + incl - bt;
+            const uint32_t qend = qbase + __shfl_sync(0xFFFFFFFFu, incl, 31);
+
+            // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
+            // fast path: a staging word has at most two owners (needs >= 32 bits from every lane) and
+            // every group fits the 32-bit window
+            const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u && (!CHECK || (ormask & ~31u) == 0u));
+            if (fast) {
+                uint32_t r = q0 & 31u;                        // bits already in the word being filled
+                uint32_t wi = head + (q0 >> 5);               // that word's ring position
+                uint32_t lo_prev = 0;
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    r += gss[g];
+                    if (r >= 32u) {
+                        // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
+                        // before this group, the rest from the window after it (funnel shifts use r mod 32)
+                        const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
+                        ring[wi & kRingMask] = __funnelshift_r(los[g], hi, r);
+                        wi++;
+                        r -= 32u;
+                    }
+                    lo_prev = los[g];
+                }
+                const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
+                uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
+                if (lane == 0) left_tail = prev_tail;         // the previous sub-block's last partial word
+                if (q0 & 31u) ring[(head + (q0 >> 5)) & kRingMask] |= left_tail;   // my head word, completed by me
+                prev_tail = __shfl_sync(0xFFFFFFFFu, tailw, 31);
+                if (lane == 31 && r) ring[(head + (qend >> 5)) & kRingMask] = tailw;
+            } else {
+                // words that begin inside this sub-block start from zero; the word shared with the previous
+                // sub-block already holds its bits
+                for (uint32_t j = ((qbase + 31u) >> 5) + lane; j < ((qend + 31u) >> 5); j += 32u)
+                    ring[(head + j) & kRingMask] = 0u;
+                __syncwarp();
+                uint32_t q = q0, lo = 0;
+#pragma unroll 1
+                for (int i = 0; i < S; i++) {
+                    if (sym0 + i < n_bytes) {
+                        uint32_t cwl, l;
+                        fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
+                        if (l) {
+                            const uint32_t ln = __funnelshift_l(cwl, lo, l);
+                            const uint32_t qn = q + l;
+                            if ((qn ^ q) & ~31u)
+                                atomicOr(&ring[(head + (qn >> 5) - 1u) & kRingMask],
+                                         __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
+                            q = qn;
+                            lo = ln;
+                        }
+                    }
+                }
+                const uint32_t f = q & 31u;
+                if (f) atomicOr(&ring[(head + (q >> 5)) & kRingMask], lo << (32u - f));
+                __syncwarp();
+                prev_tail = (qend & 31u) ? ring[(head + (qend >> 5)) & kRingMask] : 0u;
+            }
+            qbase = qend;
+            __syncwarp();                                     // orders this sub-block's ring writes before the next one's
+            prof.add(kProfEmit, t0);
+
+            full = full_next;
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = wn[i];
         }
         __syncwarp();
 
-        // ---------------- carry: the last (<= 31) bits of this chunk, for the right-hand neighbour ----------------
+        // ---------------- the chunk is staged: count, carry, hand-offs ----------------
+        const uint32_t n = qbase;
         if (lane == 0) {
+            // carry: the last (<= 31) bits of this chunk, for the right-hand neighbour
             uint32_t val = 0;
             if (n) {
                 const uint32_t a = (n - 1u) >> 5, r = n & 31u;
-                const uint32_t w1 = st[a], w0 = a ? st[a - 1u] : 0u;
+                const uint32_t w1 = ring[(head + a) & kRingMask], w0 = a ? ring[(head + a - 1u) & kRingMask] : 0u;
                 val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
             }
             ctrl->carry_val[k & 15u][warp] = val;
             ctrl->carry_cnt[k & 15u][warp] = n < 31u ? n : 31u;
-            ctrl->chunk[warp][slot] = make_uint2(start, n);
+            ctrl->chunk[warp][slot] = make_uint2(head, n);
+            ctrl->sums[slot][warp] = n;
+            mbar_arrive(&ctrl->bar_sums[slot]);
             mbar_arrive(&ctrl->bar_emit[slot]);
         }
+        head += n ? ((n + 31u) >> 5) : 1u;
         emitted++;
         __syncwarp();
-        prof.add(kProfEmit, t0);
 
         // ---------------- copy out every chunk whose global offset is already known ----------------
         while (retired < emitted && mbar_test(&ctrl->bar_prefix[slot_of(retired)], par_of(retired)))
             retire(false);
 
         tile = tnext;
-        full = full_next;
-#pragma unroll
-        for (int i = 0; i < 8; i++) w[i] = wn[i];
     }
     while (retired < emitted) retire(true);
     prof.add(kProfWorker, t_worker);

@@ -21,7 +21,7 @@ import torch.distributed as dist
 from .encoder import bits_from_hist, build_codebook, shard_offsets
 
 
-def shard_bounds(n_words, world, tile_words=4096):
+def shard_bounds(n_words, world, tile_words=8192):
     """Contiguous word ranges, boundaries on encode-tile multiples (last shard takes the ragged end)."""
     tiles = (n_words + tile_words - 1) // tile_words
     per = (tiles + world - 1) // world

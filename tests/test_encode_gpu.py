@@ -8,7 +8,7 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TILE = 16384          # hb::kTileBytes: 16 worker warps x 1 KiB chunks
+TILE = 32768          # hb::kTileBytes: 16 worker warps x 2 KiB chunks (two 1 KiB sub-blocks)
 
 
 @pytest.fixture(scope="module")
@@ -160,7 +160,7 @@ def random_prefix_code(rng, nsym, skew):
 
 @pytest.mark.parametrize("skew,nsym", [("geo", 2), ("geo", 22), ("geo", 64), ("geo", 256), ("flat", 256),
                                        ("flat", 3), ("fib", 17), ("fib", 25), ("fib", 32)])
-@pytest.mark.parametrize("n_bytes", [4, 1020, 1024, 16380, 16384, 16388, 3 * 16384 + 20, 1_000_000,
+@pytest.mark.parametrize("n_bytes", [4, 1020, 1024, 1028, 2048, 16380, 32764, 32768, 32772, 3 * 32768 + 20, 1_000_000,
                                      5 * 1024 * 1024 + 4])
 def test_random_codebooks(hb, enc, orc, torch_mod, skew, nsym, n_bytes):
     import zlib
@@ -312,7 +312,7 @@ def test_vlc_encode_drop_in_signature(hb, orc, ref, c1):
         assert r_size == outsize and np.array_equal(r_out[:nw], out[:nw])
 
 
-@pytest.mark.parametrize("n_bytes,chunk_mib", [(64 << 20, None), ((3 << 20) + 16388, 1), (16384, 1), (4, 1)])
+@pytest.mark.parametrize("n_bytes,chunk_mib", [(64 << 20, None), ((3 << 20) + 32772, 1), (32768, 1), (4, 1)])
 def test_encode_host_chunked(hb, enc, orc, torch_mod, monkeypatch, n_bytes, chunk_mib):
     """H2D -> chunked launches over ONE job -> D2H must equal the single-launch stream"""
     w = hb.workloads.get("c5")
