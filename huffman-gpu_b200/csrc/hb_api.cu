@@ -28,8 +28,6 @@ struct hb_ctx {
     unsigned long long *d_tree[2] = {nullptr, nullptr};   // look-back Fenwick trees, used by alternate jobs
     uint64_t tree_dirty[2] = {0, 0};          // entries a job left non-zero (cleared by the next job's kernel)
     int tree_cur = 0;
-    unsigned long long *d_ticket = nullptr;   // monotonically increasing tile ticket
-    uint64_t ticket_base = 0;
 
     uint32_t *d_table = nullptr;              // 512 words: packed[256] or wide uint2[256]
     uint32_t *h_table = nullptr;              // pinned staging for the table upload
@@ -191,8 +189,6 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
         ctx->tree_dirty[ctx->tree_cur ^ 1] = 0;
         ctx->tree_dirty[ctx->tree_cur] = p.n_tiles;
     }
-    p.ticket = ctx->d_ticket;
-    p.ticket_base = ctx->ticket_base;
     p.table = ctx->d_table;
     p.result = ctx->h_result;
     p.prof = ctx->d_prof;
@@ -202,7 +198,6 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
     uint64_t grid = (uint64_t)ctx->sm_count;
     if (grid > tiles) grid = tiles;
     HB_CUDA(ctx, hb::launch_encode(ctx->variant, p, (int)grid, stream));
-    ctx->ticket_base += tiles + grid;      // every CTA draws exactly one ticket past the end
     ctx->launches++;
     return HB_OK;
 }
@@ -247,8 +242,6 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
         ok = ok && cudaMalloc(&ctx->d_tree[i], ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
         ok = ok && cudaMemset(ctx->d_tree[i], 0, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
     }
-    ok = ok && cudaMalloc(&ctx->d_ticket, sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMemset(ctx->d_ticket, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_table, 512 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_table, 512 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaHostAlloc(&ctx->h_result, sizeof(hb::EncResult), cudaHostAllocMapped) == cudaSuccess;
@@ -294,7 +287,6 @@ void hb_free(hb_ctx *ctx)
     }
     cudaFree(ctx->d_tree[0]);
     cudaFree(ctx->d_tree[1]);
-    cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_table);
     if (ctx->h_table) cudaFreeHost(ctx->h_table);
     if (ctx->h_result) cudaFreeHost(ctx->h_result);

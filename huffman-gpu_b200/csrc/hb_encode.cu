@@ -11,9 +11,11 @@
  * instruction issue, not by HBM, so everything is arranged to spend as few issue slots per symbol
  * as possible and to never leave a warp waiting on another one:
  *
- *   - one persistent CTA per SM: 16 autonomous WORKER warps, a PUBLISHER warp and a RESOLVER warp.
- *     Tiles of 16 KiB are handed out by an atomic ticket counter; a worker warp owns a 1 KiB chunk
- *     of each tile (32 contiguous symbols per lane, one 256-bit load, prefetched one tile ahead);
+ *   - one persistent CTA per SM (a cooperative launch: all CTAs are co-resident): 16 autonomous WORKER
+ *     warps, a PUBLISHER warp and two RESOLVER warps.  CTA b takes tiles b, b + grid, b + 2 grid, ... of
+ *     32 KiB, so the tiles in flight at any time are consecutive; a worker warp owns a 2 KiB chunk of each
+ *     tile, processed as two 1 KiB sub-blocks (32 contiguous symbols per lane, one 256-bit load per lane,
+ *     prefetched one sub-block ahead);
  *   - the codebook lives in shared memory at a 256-byte stride per symbol, replicated per lane:
  *     ONE byte-permute builds the whole lookup address (symbol -> byte 1, lane*4 -> byte 0) and
  *     the lookup is bank-conflict free for any symbol distribution.  An entry is
@@ -72,7 +74,6 @@ constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 //   [rings of workers 0..5 | pad] up to the boundary, [table 64 KiB], [rings of workers 6..15], [control].
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
 constexpr uint32_t kTabOffset = 65536 - kSmemReserved;  // table offset inside the dynamic block
-constexpr int kAhead = 3;                               // tile tickets drawn ahead of the slowest worker
 constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
 constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
 constexpr uint32_t kRingMask = kRingWords - 1;
@@ -88,9 +89,6 @@ struct Ctrl {
     unsigned long long bar_agg[kDepth];         // publisher -> resolver: aggregate of tile k published
     unsigned long long bar_prefix[kDepth];      // resolver -> workers: global offset of tile k resolved
     unsigned long long bar_emit[kDepth];        // workers -> workers: chunk carries of tile k posted
-    unsigned long long bar_tile[8];             // publisher -> workers: ring[k & 7] holds the k-th tile id
-    unsigned long long ring[8];
-    unsigned long long sq[16];                  // the same sequence for the resolvers (longer lived)
     unsigned long long prefix[kDepth];
     uint32_t prev[kDepth];
     uint32_t flags[kDepth];
@@ -105,6 +103,12 @@ struct Ctrl {
 // position k of a CTA's tile sequence -> slot k % kDepth and mbarrier parity (k / kDepth) & 1
 __device__ __forceinline__ uint32_t slot_of(uint32_t k) { return k & (uint32_t)(kDepth - 1); }
 __device__ __forceinline__ uint32_t par_of(uint32_t k) { return (k / (uint32_t)kDepth) & 1u; }
+// the k-th tile of this CTA (static interleave: the tiles in flight across the grid are consecutive)
+__device__ __forceinline__ unsigned long long tile_of(const EncParams &p, uint32_t k)
+{
+    const unsigned long long t = p.first_tile + (unsigned long long)k * gridDim.x + blockIdx.x;
+    return t < p.end_tile ? t : kNoTile;
+}
 
 // ---- small PTX helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
@@ -274,50 +278,15 @@ __device__ uint32_t bits_before(const EncParams &p, uint32_t tab_s, unsigned lon
     return acc;
 }
 
-// ---- publisher warp: tickets and tile aggregates ---------------------------------------------------------
+// ---- publisher warp: tile aggregates -----------------------------------------------------------------------
 // Never waits on another CTA: as soon as the 16 chunk counts of a tile are in, their sum goes into the
 // tree, whatever state this CTA's own look-backs are in.
 __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
 {
-    bool ended = false;
-    auto draw = [&]() -> unsigned long long {            // raw ticket; its latency is hidden until first use
-        unsigned long long tk = 0;
-        if (lane == 0 && !ended) tk = atomicAdd(p.ticket, 1ULL);
-        return tk;
-    };
-    // k-th tile of this CTA: ring[k & 7] for the workers, sq[k & 15] for the resolvers.  Tickets run
-    // kAhead positions ahead of the slowest worker, so a fast worker is not held up by a slow one.
-    auto post = [&](uint32_t k, unsigned long long raw) -> unsigned long long {
-        unsigned long long t = kNoTile;
-        if (!ended) {
-            t = __shfl_sync(0xFFFFFFFFu, raw, 0) - p.ticket_base + p.first_tile;
-            if (t >= p.end_tile) {
-                t = kNoTile;
-                ended = true;           // exactly one ticket past the end per CTA
-            }
-        }
-        if (lane == 0) {
-            ctrl->ring[k & 7u] = t;
-            ctrl->sq[k & 15u] = t;
-            mbar_arrive(&ctrl->bar_tile[k & 7u]);
-        }
-        return t;
-    };
-
-    for (uint32_t j = 0; j < (uint32_t)kAhead; j++) post(j, draw());
-    __syncwarp();
     for (uint32_t k = 0;; k++) {
         const uint32_t slot = slot_of(k);
-        const unsigned long long t_cur = ctrl->sq[k & 15u];
-        if (t_cur == kNoTile) {
-            // wake both resolvers (positions k and k + 1), which then stop too
-            if (lane == 0) {
-                mbar_arrive(&ctrl->bar_agg[slot]);
-                mbar_arrive(&ctrl->bar_agg[slot_of(k + 1u)]);
-            }
-            break;
-        }
-        const unsigned long long raw = draw();                       // position k + kAhead
+        const unsigned long long t_cur = tile_of(p, k);
+        if (t_cur == kNoTile) break;
         mbar_wait(&ctrl->bar_sums[slot], par_of(k));
 
         // exclusive scan of the 16 chunk bit counts
@@ -337,8 +306,6 @@ __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
             for (uint32_t j = 0; j < lane && i < p.n_tiles; j++) i += i & (0ULL - i);
             if (i < p.n_tiles) red_add_u64(&p.tree[i], kTreeOne | (unsigned long long)btile);
         }
-        // every worker is past pass 1 of tile k, so ring[(k + kAhead) & 7] (tile k + kAhead - 8) is dead
-        post(k + (uint32_t)kAhead, raw);
         __syncwarp();
         if (lane == 0) {
             ctrl->btile[slot] = btile;
@@ -365,14 +332,14 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
     uint32_t sym = 0;
     for (uint32_t k = first;; k += 2u) {
         const uint32_t slot = slot_of(k);
+        const unsigned long long tile = tile_of(p, k);
+        if (tile == kNoTile) break;
+        if (k == first) sym = tail_symbol(tile);
+        // this warp's next tile: its tail symbols have two tiles to land
+        const uint32_t sym_next = tail_symbol(tile_of(p, k + 2u));
         long long t0 = prof.now();
         mbar_wait(&ctrl->bar_agg[slot], par_of(k));
         prof.add(kProfWaitAgg, t0);
-        const unsigned long long tile = ctrl->sq[k & 15u];
-        if (tile == kNoTile) break;
-        if (k == first) sym = tail_symbol(tile);
-        // this warp's next tile: its tail symbols have two tiles to land (sq[k + 2] is posted before agg[k - 2])
-        const uint32_t sym_next = tail_symbol(ctrl->sq[(k + 2u) & 15u]);
         prof.count(kProfTiles);
 
         // ---------------- look-back: the <= log2(n) tree nodes that tile the prefix [0, tile) ----------------
@@ -530,8 +497,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
     };
 
     uint32_t w[8], wn[8];
-    mbar_wait(&ctrl->bar_tile[0], 0);
-    unsigned long long tile = ctrl->ring[0];
+    unsigned long long tile = tile_of(p, 0);
     bool full = tile != kNoTile && sub_index(tile, 0) < full_subs;
     if (full) ld_stream_v8(in_lane + sub_index(tile, 0) * 256ULL, w);
 
@@ -541,9 +507,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         if (emitted - retired >= (uint32_t)kDepth) retire(true);
 
         long long t0 = prof.now();
-        mbar_wait(&ctrl->bar_tile[(k + 1u) & 7u], ((k + 1u) >> 3) & 1u);
-        prof.add(kProfWaitTile, t0);
-        const unsigned long long tnext = ctrl->ring[(k + 1u) & 7u];
+        const unsigned long long tnext = tile_of(p, k + 1u);
 
         uint32_t qbase = 0;                                    // bits of this chunk emitted so far
         uint32_t prev_tail = 0;                                // the partial word that ends at qbase (left-aligned)
@@ -745,7 +709,6 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
             mbar_init(&ctrl->bar_agg[i], 1);
             mbar_init(&ctrl->bar_prefix[i], 1);
         }
-        for (int i = 0; i < 8; i++) mbar_init(&ctrl->bar_tile[i], 1);
     }
     __syncthreads();
 
@@ -882,8 +845,13 @@ cudaError_t launch_encode(const EncVariant &v, const EncParams &p, int grid, cud
 {
     const VariantRow *r = find_row(v);
     if (!r) return cudaErrorInvalidValue;
-    r->fn<<<grid, kEncThreads, r->smem, stream>>>(p);
-    return cudaGetLastError();
+    // Cooperative launch: the look-back makes a CTA wait for lower-numbered tiles, which are spread over the
+    // whole grid, so every CTA must be resident.  The runtime then refuses the launch instead of deadlocking
+    // if the grid cannot be co-scheduled.
+    EncParams args = p;
+    void *kargs[] = {&args};
+    return cudaLaunchCooperativeKernel((const void *)r->fn, dim3((unsigned)grid), dim3(kEncThreads), kargs,
+                                       r->smem, stream);
 }
 
 }  // namespace hb

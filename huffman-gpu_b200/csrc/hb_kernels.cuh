@@ -38,8 +38,6 @@ struct EncParams {
     unsigned long long *tree;         // Fenwick tree over the job's tile bit counts, 1-based, n_tiles entries
     unsigned long long *tree_zero;    // the tree of the next job: entries [0, zero_count) are cleared
     unsigned long long zero_count;
-    unsigned long long *ticket;       // monotonically increasing work counter (never reset)
-    unsigned long long ticket_base;   // counter value at the start of this launch
     const uint32_t *table;            // packed: uint32[256]; wide: uint2[256] as uint32[512]
     EncResult *result;
     unsigned long long *prof;         // optional cycle counters ($HB_PROFILE), else nullptr
