@@ -68,27 +68,35 @@ constexpr int kTreeCountShift = 44;
 constexpr unsigned long long kTreeOne = 1ULL << kTreeCountShift;
 constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 
-// Shared-memory map.  The table must start on a 64 KiB boundary of the CTA's shared window so that
-// the byte permute can produce a complete lookup address (window address bytes 2..3 are constants).
-// The window starts with kSmemReserved bytes owned by the system, so the dynamic block is laid out as
-//   [rings of workers 0..5 | pad] up to the boundary, [table 64 KiB], [rings of workers 6..15], [control].
+// Shared-memory map (addresses in the CTA's shared WINDOW; the dynamic block starts at kSmemReserved):
+//   0x00400  control block (mbarriers, per-tile hand-off data)
+//   0x02000  staging rings of workers 0..6      (7 x 8 KiB)
+//   0x10000  codebook table                      (64 KiB)
+//   0x20000  staging rings of workers 7..15     (9 x 8 KiB)
+// The table starts on a 64 KiB boundary so that one byte permute yields a complete lookup address (window
+// address bytes 2..3 are constants); every ring is aligned to its size so that a ring address wraps with
+// one AND/OR on the address itself.
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
-constexpr uint32_t kTabOffset = 65536 - kSmemReserved;  // table offset inside the dynamic block
+constexpr uint32_t kTabWindow = 0x10000;
+constexpr uint32_t kTabOffset = kTabWindow - kSmemReserved;          // offsets are inside the dynamic block
 constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
 constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
+constexpr uint32_t kRingBytes = kRingWords * 4;
 constexpr uint32_t kRingMask = kRingWords - 1;
+constexpr uint32_t kRingByteMask = kRingBytes - 1;
 constexpr int kRingsBelow = 7;                          // rings that fit under the table
+constexpr uint32_t kRingsBelowOffset = 0x2000 - kSmemReserved;
 constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
-constexpr uint32_t kCtrlOffset = kRingsAboveOffset + (kW - kRingsBelow) * kRingWords * 4;
-static_assert(kRingsBelow * kRingWords * 4 <= kTabOffset, "rings 0..6 must fit below the table");
+constexpr uint32_t kCtrlOffset = 0;
+constexpr uint32_t kSmemBytes = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
+static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes == kTabOffset, "rings 0..6 end where the table starts");
 // a chunk is staged contiguously (mod ring size) and must fit even when every symbol takes the longest code
 static_assert((uint32_t)kSubBlocks * S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
 
 struct Ctrl {
-    unsigned long long bar_sums[kDepth];        // workers -> publisher: chunk bit counts of tile k posted
+    unsigned long long bar_sums[kDepth];        // workers -> publisher: chunk bit counts and carries of tile k posted
     unsigned long long bar_agg[kDepth];         // publisher -> resolver: aggregate of tile k published
     unsigned long long bar_prefix[kDepth];      // resolver -> workers: global offset of tile k resolved
-    unsigned long long bar_emit[kDepth];        // workers -> workers: chunk carries of tile k posted
     unsigned long long prefix[kDepth];
     uint32_t prev[kDepth];
     uint32_t flags[kDepth];
@@ -99,6 +107,8 @@ struct Ctrl {
     uint32_t carry_cnt[16][kW];
     uint2 chunk[kW][kDepth];                    // worker-private: {ring position, bits} of its staged chunks
 };
+
+static_assert(sizeof(Ctrl) <= kRingsBelowOffset, "the control block must fit below the first ring");
 
 // position k of a CTA's tile sequence -> slot k % kDepth and mbarrier parity (k / kDepth) & 1
 __device__ __forceinline__ uint32_t slot_of(uint32_t k) { return k & (uint32_t)(kDepth - 1); }
@@ -169,6 +179,28 @@ __device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t (&w)[8]
                    "=r"(w[7])
                  : "l"(p));
 }
+// ring access by shared-window byte address (rings are aligned to kRingBytes)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// address of ring position `pos` (an absolute word counter)
+__device__ __forceinline__ uint32_t ring_at(uint32_t ring_s, uint32_t pos)
+{
+    return ring_s | ((pos << 2) & kRingByteMask);
+}
+// advance a ring address by `bytes`, wrapping inside the ring
+__device__ __forceinline__ uint32_t ring_step(uint32_t ring_s, uint32_t addr, uint32_t bytes)
+{
+    return ring_s | ((addr + bytes) & kRingByteMask);
+}
+
 // ---- optional cycle accounting: build with -DHB_PROFILE and run with $HB_PROFILE=1 --------------------
 enum { kProfWaitTile = 0, kProfWaitPrefix, kProfWorker, kProfWaitSums, kProfWaitAgg, kProfLookback,
        kProfBitsBefore, kProfResolver, kProfTiles, kProfPolls, kProfPass1, kProfEmit, kProfCopy, kProfCount };
@@ -407,8 +439,34 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
 }
 
 // ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
-// The chunk occupies ring words start, start+1, ... (mod kRingWords).
-__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const uint32_t *ring, uint32_t start,
+// `cnt` output words from a run of staged words that does not wrap: out[j] = the 32 bits that start `sh`
+// bits before staged word j; word 0 takes those leading bits from `first_before`.
+__device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t cnt, uint32_t first_before,
+                                         uint32_t sh, uint32_t lane)
+{
+    uint32_t a = src_s + lane * 4u;
+    uint32_t *o = out + lane;
+    uint32_t j = lane;
+    if (j < cnt) {                                             // peeled: only word 0 lacks a staged predecessor
+        const uint32_t before = j ? lds_u32(a - 4u) : first_before;
+        *o = __funnelshift_r(lds_u32(a), before, sh);
+    }
+    for (j += 32u; j + 32u < cnt; j += 64u) {                  // two words per lane per trip
+        a += 256u;
+        o += 64;
+        const uint32_t c0 = lds_u32(a - 128u), b0 = lds_u32(a - 132u);
+        const uint32_t c1 = lds_u32(a), b1 = lds_u32(a - 4u);
+        o[-32] = __funnelshift_r(c0, b0, sh);
+        o[0] = __funnelshift_r(c1, b1, sh);
+    }
+    if (j < cnt) {
+        a += 128u;
+        o[32] = __funnelshift_r(lds_u32(a), lds_u32(a - 4u), sh);
+    }
+}
+
+// The chunk occupies ring positions start, start+1, ... (mod kRingWords); `ring_s` is the ring's window address.
+__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, uint32_t ring_s, uint32_t start,
                                          uint32_t k, uint32_t n, uint32_t warp, uint32_t lane)
 {
     const uint32_t slot = slot_of(k);
@@ -427,20 +485,20 @@ __device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const u
     const uint32_t nfull = (uint32_t)((end >> 5) - g0);        // words whose last bit is ours (<= ceil(n/32))
     const bool last = ctrl->flags[slot] && warp == (uint32_t)kW - 1;   // the job's final word(s)
     if (!last && g0 + nfull <= p.out_cap_words) {
-        // common case: every word this chunk owns comes from two neighbouring staged words
+        // common case: every word this chunk owns comes from two neighbouring staged words; the staged run
+        // wraps around the ring at most once
         uint32_t *out = p.out + g0;
-#pragma unroll 2
-        for (uint32_t j = lane; j < nfull; j += 32u) {
-            const uint32_t before = j ? ring[(start + j - 1u) & kRingMask] : cin;
-            out[j] = __funnelshift_r(ring[(start + j) & kRingMask], before, sh);
-        }
+        const uint32_t s0 = start & kRingMask;
+        const uint32_t run0 = min(nfull, kRingWords - s0);
+        copy_run(out, ring_s + s0 * 4u, run0, cin, sh, lane);
+        if (run0 < nfull) copy_run(out + run0, ring_s, nfull - run0, lds_u32(ring_s + kRingBytes - 4u), sh, lane);
     } else {
         const uint32_t nwrite = nfull + (last ? 1u : 0u);
         const uint32_t nstage = (n + 31u) >> 5;
         bool spill = false;
         for (uint32_t j = lane; j < nwrite; j += 32u) {
-            const uint32_t cur = (j < nstage) ? ring[(start + j) & kRingMask] : 0u;
-            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? ring[(start + j - 1u) & kRingMask] : 0u);
+            const uint32_t cur = (j < nstage) ? lds_u32(ring_at(ring_s, start + j)) : 0u;
+            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? lds_u32(ring_at(ring_s, start + j - 1u)) : 0u);
             const uint32_t v = __funnelshift_r(cur, before, sh);
             if (g0 + j < p.out_cap_words)
                 p.out[g0 + j] = v;
@@ -453,7 +511,7 @@ __device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, const u
 
 // ---- worker warp ----------------------------------------------------------------------------------------
 template <int G, bool WIDE, bool CHECK>
-__device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl *ctrl, uint32_t warp,
+__device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl *ctrl, uint32_t warp,
                        uint32_t lane)
 {
     constexpr int NG = (S + G - 1) / G;
@@ -462,6 +520,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
     const uint32_t laneoff = lane * 4u | ((tab_s >> 16) << 8);
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     const unsigned long long n_bytes = p.n_words * 4ULL;
+    // the warp scan adds a neighbour's value when lane >= distance: as multiplicands for one IMAD per step
+    uint32_t scan_on[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) scan_on[i] = lane >= (1u << i) ? 1u : 0u;
 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
@@ -472,24 +534,22 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
     auto retire = [&](bool blocking) {
         const uint32_t k = retired, slot = slot_of(k);
         {
-            // the offset needs every worker's count (pass 1), the carries every worker's bits (pass 2): the
-            // second is almost always in by the time the first has been through the look-back
+            // the offset needs every worker's count, the carries every worker's bits: both are posted together
             const long long t0 = prof.now();
             if (blocking) mbar_wait(&ctrl->bar_prefix[slot], par_of(k));
-            mbar_wait(&ctrl->bar_emit[slot], par_of(k));
             prof.add(kProfWaitPrefix, t0);
         }
         const long long t0 = prof.now();
         const uint2 ch = ctrl->chunk[warp][slot];
-        copy_out(p, ctrl, ring, ch.x, k, ch.y, warp, lane);
+        copy_out(p, ctrl, ring_s, ch.x, k, ch.y, warp, lane);
         retired++;
         tail = (retired < emitted) ? ctrl->chunk[warp][slot_of(retired)].x : head;
         __syncwarp();
         prof.add(kProfCopy, t0);
     };
 
-    // sub-block j (0 .. kSub-1) of this warp's chunk of tile t starts at word (t * kSub * kW + warp * kSub + j) * 256;
-    // a sub-block is `full` when it lies entirely inside the input
+    // sub-block j (0 .. kSub-1) of this warp's chunk of tile t is global sub-block (t * kW + warp) * kSub + j,
+    // 256 words each; a sub-block is `full` when it lies entirely inside the input
     const unsigned long long full_subs = p.n_words / 256ULL;     // global sub-block indices below this are full
     const uint32_t *in_lane = p.in + lane * 8u;
     auto sub_index = [&](unsigned long long t, uint32_t j) {
@@ -505,8 +565,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
         const uint32_t k = emitted, slot = slot_of(k);
         // slot k % kDepth still belongs to tile k - kDepth until that one has been copied out
         if (emitted - retired >= (uint32_t)kDepth) retire(true);
-
-        long long t0 = prof.now();
         const unsigned long long tnext = tile_of(p, k + 1u);
 
         uint32_t qbase = 0;                                    // bits of this chunk emitted so far
@@ -522,14 +580,13 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
             // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old.
 #pragma unroll
             for (int i = 0; i < 8; i++) asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
-            t0 = prof.now();
+            long long t0 = prof.now();
             const bool last_sub = sub + 1u == (uint32_t)kSub;
             const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
             const bool full_next = (!last_sub || tnext != kNoTile) && nsub < full_subs;
             if (full_next) ld_stream_v8(in_lane + nsub * 256ULL, wn);
 
             // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
-            const unsigned long long sym0 = sub_index(tile, sub) * 1024ULL + lane * (uint32_t)S;   // slow paths only
             uint32_t los[NG], gss[NG];
             uint32_t bt = 0, ormask = 0;
             if (full) {
@@ -557,6 +614,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
                     }
                 }
             } else {
+                const unsigned long long sym0 = sub_index(tile, sub) * 1024ULL + lane * (uint32_t)S;
 #pragma unroll 1
                 for (int i = 0; i < S; i++) {
                     if (sym0 + i < n_bytes) {
@@ -574,10 +632,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
             // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
             uint32_t incl = bt;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                if (lane >= (uint32_t)d) incl += v;
-            }
+            for (int i = 0; i < 5; i++) incl += __shfl_up_sync(0xFFFFFFFFu, incl, 1u << i) * scan_on[i];
             const uint32_t q0 = qbase + incl - bt;
             const uint32_t qend = qbase + __shfl_sync(0xFFFFFFFFu, incl, 31);
 
@@ -587,7 +642,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
             const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u && (!CHECK || (ormask & ~31u) == 0u));
             if (fast) {
                 uint32_t r = q0 & 31u;                        // bits already in the word being filled
-                uint32_t wi = head + (q0 >> 5);               // that word's ring position
+                const uint32_t wa0 = ring_at(ring_s, head + (q0 >> 5));
+                uint32_t wa = wa0;                            // that word's address
                 uint32_t lo_prev = 0;
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
@@ -596,8 +652,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
                         // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
                         // before this group, the rest from the window after it (funnel shifts use r mod 32)
                         const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                        ring[wi & kRingMask] = __funnelshift_r(los[g], hi, r);
-                        wi++;
+                        sts_u32(wa, __funnelshift_r(los[g], hi, r));
+                        wa = ring_step(ring_s, wa, 4u);
                         r -= 32u;
                     }
                     lo_prev = los[g];
@@ -605,15 +661,17 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
                 const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
                 uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
                 if (lane == 0) left_tail = prev_tail;         // the previous sub-block's last partial word
-                if (q0 & 31u) ring[(head + (q0 >> 5)) & kRingMask] |= left_tail;   // my head word, completed by me
+                if (q0 & 31u) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
                 prev_tail = __shfl_sync(0xFFFFFFFFu, tailw, 31);
-                if (lane == 31 && r) ring[(head + (qend >> 5)) & kRingMask] = tailw;
+                if (lane == 31 && r) sts_u32(wa, tailw);      // wa == the word that holds bit qend
             } else {
+                const unsigned long long sym0 = sub_index(tile, sub) * 1024ULL + lane * (uint32_t)S;
                 // words that begin inside this sub-block start from zero; the word shared with the previous
                 // sub-block already holds its bits
                 for (uint32_t j = ((qbase + 31u) >> 5) + lane; j < ((qend + 31u) >> 5); j += 32u)
-                    ring[(head + j) & kRingMask] = 0u;
+                    sts_u32(ring_at(ring_s, head + j), 0u);
                 __syncwarp();
+                uint32_t *ring = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(ring_s));
                 uint32_t q = q0, lo = 0;
 #pragma unroll 1
                 for (int i = 0; i < S; i++) {
@@ -634,7 +692,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
                 const uint32_t f = q & 31u;
                 if (f) atomicOr(&ring[(head + (q >> 5)) & kRingMask], lo << (32u - f));
                 __syncwarp();
-                prev_tail = (qend & 31u) ? ring[(head + (qend >> 5)) & kRingMask] : 0u;
+                prev_tail = (qend & 31u) ? lds_u32(ring_at(ring_s, head + (qend >> 5))) : 0u;
             }
             qbase = qend;
             __syncwarp();                                     // orders this sub-block's ring writes before the next one's
@@ -644,7 +702,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
 #pragma unroll
             for (int i = 0; i < 8; i++) w[i] = wn[i];
         }
-        __syncwarp();
 
         // ---------------- the chunk is staged: count, carry, hand-offs ----------------
         const uint32_t n = qbase;
@@ -653,7 +710,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
             uint32_t val = 0;
             if (n) {
                 const uint32_t a = (n - 1u) >> 5, r = n & 31u;
-                const uint32_t w1 = ring[(head + a) & kRingMask], w0 = a ? ring[(head + a - 1u) & kRingMask] : 0u;
+                const uint32_t w1 = lds_u32(ring_at(ring_s, head + a));
+                const uint32_t w0 = a ? lds_u32(ring_at(ring_s, head + a - 1u)) : 0u;
                 val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
             }
             ctrl->carry_val[k & 15u][warp] = val;
@@ -661,7 +719,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t *ring, Ctrl 
             ctrl->chunk[warp][slot] = make_uint2(head, n);
             ctrl->sums[slot][warp] = n;
             mbar_arrive(&ctrl->bar_sums[slot]);
-            mbar_arrive(&ctrl->bar_emit[slot]);
         }
         head += n ? ((n + 31u) >> 5) : 1u;
         emitted++;
@@ -687,7 +744,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     uint32_t *tab = reinterpret_cast<uint32_t *>(base + kTabOffset);
     Ctrl *ctrl = reinterpret_cast<Ctrl *>(base + kCtrlOffset);
     const uint32_t tab_s = smem_addr(tab);
-    if (tab_s & 0xFFFFu) {
+    if (tab_s != kTabWindow) {
         // the shared window is not laid out as assumed: refuse loudly instead of mis-encoding
         if (threadIdx.x == 0) p.result->overflow = 2ULL;
         return;
@@ -705,7 +762,6 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     if (tid == 0) {
         for (int i = 0; i < kDepth; i++) {
             mbar_init(&ctrl->bar_sums[i], kW);
-            mbar_init(&ctrl->bar_emit[i], kW);
             mbar_init(&ctrl->bar_agg[i], 1);
             mbar_init(&ctrl->bar_prefix[i], 1);
         }
@@ -713,10 +769,10 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     __syncthreads();
 
     if (warp < (uint32_t)kW) {
-        uint32_t *ring = warp < (uint32_t)kRingsBelow
-                             ? smem + warp * kRingWords
-                             : reinterpret_cast<uint32_t *>(base + kRingsAboveOffset) + (warp - kRingsBelow) * kRingWords;
-        worker<G, WIDE, CHECK>(p, tab_s, ring, ctrl, warp, lane);
+        uint32_t *ring = reinterpret_cast<uint32_t *>(
+            warp < (uint32_t)kRingsBelow ? base + kRingsBelowOffset + warp * kRingBytes
+                                         : base + kRingsAboveOffset + (warp - kRingsBelow) * kRingBytes);
+        worker<G, WIDE, CHECK>(p, tab_s, smem_addr(ring), ctrl, warp, lane);
     } else if (warp == (uint32_t)kPublisherWarp) {
         publisher(p, ctrl, lane);
     } else {
@@ -727,7 +783,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
 template <bool WIDE>
 constexpr size_t smem_bytes()
 {
-    return (size_t)kCtrlOffset + sizeof(Ctrl);
+    return (size_t)kSmemBytes;
 }
 
 // ---- variant table ------------------------------------------------------------------------------------
