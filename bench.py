@@ -42,13 +42,17 @@ def measured_hbm_peak():
 
 
 def known_traffic(workload, variant):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, if any."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the encode kernel, from the committed
+    `ncu --set full` capture of this workload (profiles/traffic.json), or None when there is none."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        return t.get(workload, {}).get("dram_bytes_per_launch")
+        e = t.get(workload)
+        if e and e.get("kernel_variant") in (None, variant):
+            return e.get("dram_bytes_per_launch")
     except Exception:
-        return None
+        pass
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -189,15 +193,26 @@ def run_reference_arm(args):
     import huffman_gpu_b200 as hb
     wl = workload_for(args, hb)
     total = wl.n_bytes if wl is not None else 1 << 20
-    sample = min(total, args.cpu_sample_mib << 20)
+    run, kind = cpu_reference_encoder()
+    # a bounded sample per step: calibrate on 8 MiB, then size the step so that K + W steps take ~budget seconds
+    cal = host_sample(hb, wl, min(total, 8 << 20))
+    chist = np.bincount(cal, minlength=256).astype(np.uint64)
+    ccw, ccl, _ = hb.build_codebook(chist)
+    cbits = hb.bits_from_hist(chist, ccl)
+    run(cal.view(np.uint32), ccw, ccl, cbits)
+    c0 = time.perf_counter()
+    run(cal.view(np.uint32), ccw, ccl, cbits)
+    rate = cal.size / (time.perf_counter() - c0)                         # bytes/s of this box, one core
+    want = int(args.cpu_budget_s * rate / max(1, args.steps + args.warmup))
+    sample = max(1 << 20, min(total, args.cpu_sample_mib << 20, want))
+    sample -= sample % hb.capi.TILE_BYTES if sample >= hb.capi.TILE_BYTES else 0
     data = host_sample(hb, wl, sample)
     hist = np.bincount(data, minlength=256).astype(np.uint64)
     cw, cl, max_len = hb.build_codebook(hist)
     bits = hb.bits_from_hist(hist, cl)
-    run, kind = cpu_reference_encoder()
     words = data.view(np.uint32)
     for _ in range(args.warmup):
-        run(words[: min(words.size, 1 << 20)], cw, cl, bits)
+        run(words, cw, cl, bits)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         run(words, cw, cl, bits)
@@ -209,11 +224,11 @@ def run_reference_arm(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
         "data": "synthetic",
         "config": {"workload": describe(wl, args), "input_bytes_per_step": sample,
-                   "sample": "first %d MiB of the workload per step" % (sample >> 20)},
+                   "sample": "first %.1f MiB of the workload per step" % (sample / 2.0 ** 20)},
         "cpu_baseline": {"value": gbps, "unit": UNIT, "cores": 1, "kind": kind,
-                         "sample": "first %d MiB of %s, %d steps; cpu_vlc_encode is serial "
-                                   "(cpuencode.cpp:18,38) so 1 of %d host cores"
-                                   % (sample >> 20, args.workload, args.steps, os.cpu_count())},
+                         "sample": "first %.1f MiB of %s per step, %d steps; cpu_vlc_encode is serial "
+                                   "(loop-carried startbit, cpuencode.cpp:18,38): it can use 1 of the %d "
+                                   "host cores" % (sample / 2.0 ** 20, args.workload, args.steps, os.cpu_count())},
         "e2e": {"value": gbps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -230,17 +245,18 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "t1g", "c3", "c4", "c5"])
     ap.add_argument("--bytes", type=int, default=None, help="override the per-GPU input size")
     ap.add_argument("--cpu-sample-mib", type=int, default=256)
+    ap.add_argument("--cpu-budget-s", type=float, default=60.0, help="--impl reference: CPU seconds for all steps")
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=None, help="default: min(steps, 20)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                            # timing hygiene: never fewer than 3 warm-up steps
+    if args.e2e_steps is None:
+        args.e2e_steps = max(1, min(args.steps, 20))
 
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 5                         # each step is ~1.4 s of CPU work on the default sample
         return run_reference_arm(args)
 
     import torch
