@@ -146,7 +146,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             : "r"(a), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(64);                // a blocked warp must not compete for issue slots
+        __nanosleep(200);               // a blocked warp must not compete for issue slots
     }
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity)
@@ -391,7 +391,7 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
                 }
                 prof.count(kProfPolls);
                 if (!__any_sync(0xFFFFFFFFu, pending)) break;
-                __nanosleep(200);
+                __nanosleep(400);
             }
             v &= kTreeSumMask;
 #pragma unroll
@@ -523,7 +523,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
     // the warp scan adds a neighbour's value when lane >= distance: as multiplicands for one IMAD per step
     uint32_t scan_on[5];
 #pragma unroll
-    for (int i = 0; i < 5; i++) scan_on[i] = lane >= (1u << i) ? 1u : 0u;
+    for (int i = 0; i < 5; i++) {
+        scan_on[i] = lane >= (1u << i) ? 1u : 0u;
+        asm volatile("" : "+r"(scan_on[i]));                  // keep it a multiplicand (IMAD), not a compare + select
+    }
 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
@@ -577,9 +580,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             // ---------------- prefetch the next sub-block ----------------
             // Scoreboard slots count per instruction, not per register: the load below and the one that
             // filled `w` a sub-block ago are the same SASS instruction, so the first read of `w` would also
-            // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old.
-#pragma unroll
-            for (int i = 0; i < 8; i++) asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
+            // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old
+            // (the registers are copied at the end of the loop, which is a read as well; this pins the order).
+            asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[0]));    // one register is enough: one slot per load
             long long t0 = prof.now();
             const bool last_sub = sub + 1u == (uint32_t)kSub;
             const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
