@@ -1,0 +1,123 @@
+"""Sharded encode on real GPUs: every shard is encoded in global bit phase
+(start_bit = shard offset mod 32) and the stitched stream must equal the single-GPU stream and cpu_vlc_encode.
+
+  * one GPU: the shards are encoded one after the other on the same device (same kernels, same phases,
+    same stitch), which is what a rank does;
+  * two or more GPUs: torch.distributed over NCCL, one process per GPU (spawned here)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(orc, hb, n_bytes):
+    wl = hb.workloads.get("c5")
+    return orc.synth_fill(0, n_bytes, wl.seed, wl.mode, wl.nbits, wl.thr)
+
+
+@pytest.mark.parametrize("world,n_bytes", [(2, 3 * 32768 + 4096), (4, 2_000_000), (8, 8 << 20), (3, 4096)])
+def test_shards_in_global_phase_one_device(hb, orc, world, n_bytes):
+    import torch
+    from huffman_gpu_b200 import sharded
+    torch.cuda.set_device(0)
+    data = _data(orc, hb, n_bytes)
+    words = data.view(np.uint32)
+    enc = hb.Encoder(device=0, max_bytes=n_bytes)
+    hist = np.zeros(256, dtype=np.uint64)
+    bounds = sharded.shard_bounds(words.size, world)
+    d_shards, local_hists = [], []
+    for lo, hi in bounds:
+        d = torch.from_numpy(words[lo:hi].copy()).cuda() if hi > lo else torch.empty(0, dtype=torch.int32, device="cuda")
+        h = enc.histogram(d) if hi > lo else np.zeros(256, dtype=np.uint64)
+        d_shards.append(d)
+        local_hists.append(h)
+        hist += h
+    assert np.array_equal(hist, orc.histogram(data))                       # what the all-reduce would produce
+    cw, cl, _ = hb.build_codebook(hist)
+    shard_bits = np.array([hb.bits_from_hist(h, cl) for h in local_hists], dtype=np.uint64)   # the all-gather
+    starts, total = hb.shard_offsets(shard_bits)
+    ref_words, ref_bits, _ = orc.encode(words, cw, cl)
+    assert total == ref_bits
+    out = torch.zeros(total // 32 + 2, dtype=torch.int32, device="cuda")
+    for r in range(world):
+        phase = int(starts[r]) % 32
+        nw = max(1, (phase + int(shard_bits[r]) + 31) // 32)
+        part = torch.full((nw + 2,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+        bits = enc.encode(d_shards[r], cw, cl, part[: nw + 1], start_bit=phase)
+        assert bits == int(shard_bits[r])
+        if bits == 0:
+            continue
+        w0 = int(starts[r]) // 32
+        if phase:
+            enc.stitch_seam(out[w0:w0 + 1], part[:1], 1)                  # r-1's tail bits | r's head bits
+            out[w0 + 1:w0 + nw].copy_(part[1:nw])
+        else:
+            out[w0:w0 + nw].copy_(part[:nw])
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[: ref_words.size], ref_words)
+    one = torch.full((total // 32 + 2,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+    d_all = torch.from_numpy(words.copy()).cuda()
+    assert enc.encode(d_all, cw, cl, one) == ref_bits
+    assert np.array_equal(one.cpu().numpy().view(np.uint32)[: ref_words.size], ref_words)
+    enc.close()
+
+
+def _nccl_worker(rank, world, port, n_bytes, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import pyoracle
+    import huffman_gpu_b200 as hb
+    from huffman_gpu_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        orc = pyoracle.Oracle()
+        data = _data(orc, hb, n_bytes)                                    # same bytes on every rank
+        words = data.view(np.uint32)
+        lo, hi = sharded.shard_bounds(words.size, world)[rank]
+        enc = hb.Encoder(device=rank, max_bytes=max(4, (hi - lo) * 4))
+        d_in = torch.from_numpy(words[lo:hi].copy()).cuda()
+        plan = sharded.make_plan(enc.histogram(d_in), device="cuda")       # NCCL all-reduce + all-gather
+        d_out = torch.empty(plan.my_words + 2, dtype=torch.int32, device="cuda")
+        bits = enc.encode(d_in, plan.codewords, plan.codewordlens, d_out, start_bit=plan.my_phase)
+        assert bits == plan.my_bits
+        stitched = sharded.stitch_on_rank0(plan, d_out, or_fn=lambda dst, src: enc.stitch_seam(dst, src, 1))
+        if rank == 0:
+            torch.cuda.synchronize()
+            ref_words, ref_bits, _ = orc.encode(words, plan.codewords, plan.codewordlens)
+            assert ref_bits == plan.total_bits
+            got = stitched.cpu().numpy().view(np.uint32)
+            assert np.array_equal(got[: ref_words.size], ref_words)
+            ret.put("ok")
+        enc.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shards_nccl_two_gpus(native_built):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the one-device test above covers the same kernels and phases)")
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, world, port, 6 << 20, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == "ok"
