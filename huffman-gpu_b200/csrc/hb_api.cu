@@ -38,7 +38,7 @@ struct hb_ctx {
     int forced = 0;                           // $HB_FORCE_GROUP the cached table was packed under
     hb::EncVariant variant = {1, false, false};
 
-    hb::EncResult *h_result = nullptr;        // mapped pinned; the kernel writes it directly
+    hb::EncResult *h_result = nullptr;        // mapped pinned, kMaxChunks slots; the kernel writes them directly
     uint64_t pending_start_bit = 0;
     bool pending = false;
     bool pending_empty = false;
@@ -54,7 +54,7 @@ struct hb_ctx {
     uint64_t out_buf_words = 0;
     cudaStream_t s_main = nullptr;
     cudaStream_t s_d2h = nullptr;
-    cudaEvent_t ev_chunk = nullptr;
+    cudaEvent_t ev_chunk[64] = {};            // one per launch of a chunked host job
 
     unsigned long long *d_prof = nullptr;     // $HB_PROFILE: kernel cycle counters, dumped by hb_free
     uint64_t launches = 0;
@@ -167,9 +167,11 @@ int set_codebook(hb_ctx *ctx, const uint32_t cw[256], const uint32_t len[256], c
 uint64_t tiles_of(uint64_t n_words) { return (n_words + hb::kTileWords - 1) / hb::kTileWords; }
 
 // Launch the encode kernel over tiles [first_tile, end_tile) of a job.
+constexpr int kMaxChunks = 64;
+
 int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t first_tile,
                  uint64_t end_tile, uint32_t *d_out, uint64_t cap_words, uint64_t start_bit,
-                 cudaStream_t stream)
+                 cudaStream_t stream, int result_slot = 0)
 {
     hb::EncParams p;
     p.in = d_in;
@@ -190,7 +192,7 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
         ctx->tree_dirty[ctx->tree_cur] = p.n_tiles;
     }
     p.table = ctx->d_table;
-    p.result = ctx->h_result;
+    p.result = ctx->h_result + result_slot;
     p.prof = ctx->d_prof;
 
     // one persistent CTA per SM (its shared memory holds the 64 KiB table and the staging rings)
@@ -244,12 +246,13 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     }
     ok = ok && cudaMalloc(&ctx->d_table, 512 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMallocHost(&ctx->h_table, 512 * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&ctx->h_result, sizeof(hb::EncResult), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&ctx->h_result, kMaxChunks * sizeof(hb::EncResult), cudaHostAllocMapped) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_thr, 256 * sizeof(uint32_t)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_symmap, 256) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->table_uploaded, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kMaxChunks; i++)
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     if (getenv("HB_PROFILE")) {
@@ -262,8 +265,7 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
         hb_free(ctx);
         return HB_ERR_NOMEM;
     }
-    ctx->h_result->bits_end = 0;
-    ctx->h_result->overflow = 0;
+    memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
     *out = ctx;
     return HB_OK;
 }
@@ -296,7 +298,8 @@ void hb_free(hb_ctx *ctx)
     cudaFree(ctx->d_in_buf);
     cudaFree(ctx->d_out_buf);
     if (ctx->table_uploaded) cudaEventDestroy(ctx->table_uploaded);
-    if (ctx->ev_chunk) cudaEventDestroy(ctx->ev_chunk);
+    for (int i = 0; i < kMaxChunks; i++)
+        if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     (void)cudaGetLastError();
@@ -434,41 +437,55 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
         ctx->pending = false;
     }
     if ((rc = set_codebook(ctx, codewords, codewordlens, st)) != HB_OK) return rc;
-    ctx->h_result->overflow = 0;
-    ctx->h_result->bits_end = 0;
+    memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
 
     uint64_t bits = 0;
     if (n_words == 0) {
         h_out[0] = 0;                          // cpuencode.cpp:17
     } else {
         next_job(ctx);
-        // Chunked: the H2D copy of chunk k+1 overlaps the encode of chunk k.  All chunks belong to ONE
-        // job (one descriptor array, one output stream); a later launch looks back into the
-        // descriptors and symbols of the earlier ones.
+        // Chunked: the H2D copy of chunk k+1 overlaps the encode of chunk k, and the D2H copy of the words
+        // chunk k completed overlaps both (PCIe is full duplex).  All chunks belong to ONE job (one look-back
+        // tree, one output stream); a later launch looks back into the tree nodes and symbols of the earlier ones.
         const uint64_t total_tiles = tiles_of(n_words);
-        uint64_t chunk_tiles = (32ull << 20) / hb::kTileBytes;           // 32 MiB of input per chunk
+        uint64_t chunk_tiles = (32ull << 20) / hb::kTileBytes;           // 32 MiB of input per chunk ...
         static const char *env = getenv("HB_CHUNK_MIB");
         if (env && atoi(env) > 0) chunk_tiles = ((uint64_t)atoi(env) << 20) / hb::kTileBytes;
-        for (uint64_t t0 = 0; t0 < total_tiles; t0 += chunk_tiles) {
+        if (chunk_tiles < 1) chunk_tiles = 1;
+        if ((total_tiles + chunk_tiles - 1) / chunk_tiles > (uint64_t)kMaxChunks)    // ... at most kMaxChunks of them
+            chunk_tiles = (total_tiles + kMaxChunks - 1) / kMaxChunks;
+        int n_chunks = 0;
+        for (uint64_t t0 = 0; t0 < total_tiles; t0 += chunk_tiles, n_chunks++) {
             const uint64_t t1 = (t0 + chunk_tiles < total_tiles) ? t0 + chunk_tiles : total_tiles;
             const uint64_t w0 = t0 * hb::kTileWords;
             const uint64_t w1 = (t1 * hb::kTileWords < n_words) ? t1 * hb::kTileWords : n_words;
             HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_buf + w0, h_in + w0, (w1 - w0) * sizeof(uint32_t),
                                          cudaMemcpyHostToDevice, st));
-            rc = launch_tiles(ctx, ctx->d_in_buf, n_words, t0, t1, ctx->d_out_buf, dev_out_words, 0, st);
+            rc = launch_tiles(ctx, ctx->d_in_buf, n_words, t0, t1, ctx->d_out_buf, dev_out_words, 0, st, n_chunks);
             if (rc != HB_OK) return rc;
+            HB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[n_chunks], st));
         }
-        HB_CUDA(ctx, cudaStreamSynchronize(st));
-        if (ctx->h_result->overflow == 2ULL) return HB_ERR_STATE;
-        if (ctx->h_result->overflow) return HB_ERR_CAPACITY;
-        bits = ctx->h_result->bits_end;
-        // floor(bits/32)+1 words, like the reference (the word after an aligned end is zero)
-        uint64_t copy_words = bits / 32 + 1;
-        if (copy_words > out_capacity_words) copy_words = out_capacity_words;
-        if (copy_words < (bits + 31) / 32) return HB_ERR_CAPACITY;
-        HB_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_out_buf, copy_words * sizeof(uint32_t),
-                                     cudaMemcpyDeviceToHost, st));
-        HB_CUDA(ctx, cudaStreamSynchronize(st));
+        // as each launch retires, every output word below its end bit is final: send it home
+        uint64_t done_words = 0;
+        for (int c = 0; c < n_chunks; c++) {
+            HB_CUDA(ctx, cudaEventSynchronize(ctx->ev_chunk[c]));
+            if (ctx->h_result[c].overflow == 2ULL) return HB_ERR_STATE;
+            if (ctx->h_result[c].overflow) return HB_ERR_CAPACITY;
+            bits = ctx->h_result[c].bits_end;
+            // the last launch also owns the final partial word and the reference's courtesy zero word
+            uint64_t upto = (c + 1 == n_chunks) ? bits / 32 + 1 : bits / 32;
+            if (c + 1 == n_chunks) {
+                if (upto > out_capacity_words) upto = out_capacity_words;
+                if (upto < (bits + 31) / 32) return HB_ERR_CAPACITY;
+            }
+            if (upto > done_words) {
+                HB_CUDA(ctx, cudaMemcpyAsync(h_out + done_words, ctx->d_out_buf + done_words,
+                                             (upto - done_words) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                             ctx->s_d2h));
+                done_words = upto;
+            }
+        }
+        HB_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
     }
     if (total_bits) *total_bits = bits;
     if (out_bytes) *out_bytes = (bits + 7) / 8;
