@@ -58,6 +58,9 @@ namespace {
 constexpr int kW = kEncWorkers;
 constexpr int S = kSymPerThread;                        // symbols per lane per sub-block
 constexpr int kSub = kSubBlocks;
+constexpr int kLaneWords = S / 4;                        // input words per lane per sub-block
+constexpr int kSubWords = 32 * kLaneWords;               // input words per sub-block (one warp)
+static_assert(S % 32 == 0, "a lane reads whole 256-bit loads");
 constexpr int kPublisherWarp = kW;
 constexpr int kResolverWarp = kW + 1;
 constexpr int kSlotStride = 256;                        // table stride per symbol (bytes)
@@ -172,12 +175,18 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 // one 256-bit load per lane: a warp reads 1 KiB contiguous, streamed past L1 (LDG.E.256 on sm_100a)
-__device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t (&w)[8])
+__device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t *w)
 {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
                    "=r"(w[7])
                  : "l"(p));
+}
+// a lane's S contiguous symbols of one sub-block
+__device__ __forceinline__ void ld_lane(const uint32_t *p, uint32_t (&w)[kLaneWords])
+{
+#pragma unroll
+    for (int i = 0; i < kLaneWords; i += 8) ld_stream_v8(p + i, w + i);
 }
 // ring access by shared-window byte address (rings are aligned to kRingBytes)
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
@@ -515,7 +524,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                        uint32_t lane)
 {
     constexpr int NG = (S + G - 1) / G;
-    constexpr uint32_t kWorst = (uint32_t)S * (WIDE ? 31u : 24u);   // words one sub-block can emit at most
     // byte 0 = lane*4, bytes 1..2 = bytes 2..3 of the table's window address (prmt source b)
     const uint32_t laneoff = lane * 4u | ((tab_s >> 16) << 8);
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
@@ -552,17 +560,17 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
     };
 
     // sub-block j (0 .. kSub-1) of this warp's chunk of tile t is global sub-block (t * kW + warp) * kSub + j,
-    // 256 words each; a sub-block is `full` when it lies entirely inside the input
-    const unsigned long long full_subs = p.n_words / 256ULL;     // global sub-block indices below this are full
-    const uint32_t *in_lane = p.in + lane * 8u;
+    // kSubWords words each; a sub-block is `full` when it lies entirely inside the input
+    const unsigned long long full_subs = p.n_words / (unsigned long long)kSubWords;   // indices below this are full
+    const uint32_t *in_lane = p.in + lane * (uint32_t)kLaneWords;
     auto sub_index = [&](unsigned long long t, uint32_t j) {
         return (t * (unsigned long long)kW + warp) * (unsigned long long)kSub + j;
     };
 
-    uint32_t w[8], wn[8];
+    uint32_t w[kLaneWords], wn[kLaneWords];
     unsigned long long tile = tile_of(p, 0);
     bool full = tile != kNoTile && sub_index(tile, 0) < full_subs;
-    if (full) ld_stream_v8(in_lane + sub_index(tile, 0) * 256ULL, w);
+    if (full) ld_lane(in_lane + sub_index(tile, 0) * (unsigned long long)kSubWords, w);
 
     for (; tile != kNoTile;) {
         const uint32_t k = emitted, slot = slot_of(k);
@@ -574,20 +582,19 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         uint32_t prev_tail = 0;                                // the partial word that ends at qbase (left-aligned)
 #pragma unroll 1
         for (uint32_t sub = 0; sub < (uint32_t)kSub; sub++) {
-            // ---------------- room for one worst-case sub-block (older chunks leave first) ----------------
-            while (head + (qbase >> 5) + kWorst + 2u - tail > kRingWords) retire(true);
-
             // ---------------- prefetch the next sub-block ----------------
             // Scoreboard slots count per instruction, not per register: the load below and the one that
             // filled `w` a sub-block ago are the same SASS instruction, so the first read of `w` would also
             // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old
             // (the registers are copied at the end of the loop, which is a read as well; this pins the order).
-            asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[0]));    // one register is enough: one slot per load
+#pragma unroll
+            for (int i = 0; i < kLaneWords; i += 8)                       // one register per load is enough
+                asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
             long long t0 = prof.now();
             const bool last_sub = sub + 1u == (uint32_t)kSub;
             const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
             const bool full_next = (!last_sub || tnext != kNoTile) && nsub < full_subs;
-            if (full_next) ld_stream_v8(in_lane + nsub * 256ULL, wn);
+            if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, wn);
 
             // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
             uint32_t los[NG], gss[NG];
@@ -617,7 +624,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                     }
                 }
             } else {
-                const unsigned long long sym0 = sub_index(tile, sub) * 1024ULL + lane * (uint32_t)S;
+                const unsigned long long sym0 = sub_index(tile, sub) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
 #pragma unroll 1
                 for (int i = 0; i < S; i++) {
                     if (sym0 + i < n_bytes) {
@@ -639,27 +646,48 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             const uint32_t q0 = qbase + incl - bt;
             const uint32_t qend = qbase + __shfl_sync(0xFFFFFFFFu, incl, 31);
 
+            // ---------------- room in the ring for the chunk so far (older chunks leave first) ----------------
+            while (head + (qend >> 5) + 2u - tail > kRingWords) retire(true);
+
             // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
-            // fast path: a staging word has at most two owners (needs >= 32 bits from every lane) and
-            // every group fits the 32-bit window
-            const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u && (!CHECK || (ormask & ~31u) == 0u));
+            // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
+            const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
             if (fast) {
                 uint32_t r = q0 & 31u;                        // bits already in the word being filled
                 const uint32_t wa0 = ring_at(ring_s, head + (q0 >> 5));
                 uint32_t wa = wa0;                            // that word's address
                 uint32_t lo_prev = 0;
+                if (CHECK && (ormask & ~31u)) {
+                    // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one
+                    // symbol at a time -- a single codeword (< 32 bits) always fits
 #pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    r += gss[g];
-                    if (r >= 32u) {
-                        // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
-                        // before this group, the rest from the window after it (funnel shifts use r mod 32)
-                        const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                        sts_u32(wa, __funnelshift_r(los[g], hi, r));
-                        wa = ring_step(ring_s, wa, 4u);
-                        r -= 32u;
+                    for (int i = 0; i < S; i++) {
+                        const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
+                        const uint32_t cwl = tab_ld(off);
+                        const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
+                        const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
+                        r += l;
+                        if (r >= 32u) {
+                            sts_u32(wa, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), r));
+                            wa = ring_step(ring_s, wa, 4u);
+                            r -= 32u;
+                        }
+                        lo_prev = lo_new;
                     }
-                    lo_prev = los[g];
+                } else {
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        r += gss[g];
+                        if (r >= 32u) {
+                            // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
+                            // before this group, the rest from the window after it (funnel shifts use r mod 32)
+                            const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
+                            sts_u32(wa, __funnelshift_r(los[g], hi, r));
+                            wa = ring_step(ring_s, wa, 4u);
+                            r -= 32u;
+                        }
+                        lo_prev = los[g];
+                    }
                 }
                 const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
                 uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
@@ -668,7 +696,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                 prev_tail = __shfl_sync(0xFFFFFFFFu, tailw, 31);
                 if (lane == 31 && r) sts_u32(wa, tailw);      // wa == the word that holds bit qend
             } else {
-                const unsigned long long sym0 = sub_index(tile, sub) * 1024ULL + lane * (uint32_t)S;
+                const unsigned long long sym0 = sub_index(tile, sub) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
                 // words that begin inside this sub-block start from zero; the word shared with the previous
                 // sub-block already holds its bits
                 for (uint32_t j = ((qbase + 31u) >> 5) + lane; j < ((qend + 31u) >> 5); j += 32u)
@@ -703,7 +731,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
 
             full = full_next;
 #pragma unroll
-            for (int i = 0; i < 8; i++) w[i] = wn[i];
+            for (int i = 0; i < kLaneWords; i++) w[i] = wn[i];
         }
 
         // ---------------- the chunk is staged: count, carry, hand-offs ----------------
@@ -852,8 +880,8 @@ EncVariant pick_variant(const uint32_t lens[256])
     static const int wide_groups[] = {4, 2};
     const int *cand = v.wide ? wide_groups : packed_groups;
     const int ncand = v.wide ? 2 : 5;
-    // a warp falls back to the symbol-by-symbol path when any of its 32*ceil(S/G) groups is >= 32 bits;
-    // keep that below ~1% of the chunks
+    // a lane redoes its symbols one by one when any of its ceil(S/G) groups is >= 32 bits, and the other 31
+    // lanes of the warp wait for it: keep warps with such a lane below ~2%
     for (int ci = 0; ci < ncand; ci++) {
         const int G = cand[ci];
         if (G * max_len <= 31) {
@@ -879,7 +907,7 @@ EncVariant pick_variant(const uint32_t lens[256])
         }
         const double p_group = dist[32];
         const double groups_per_chunk = 32.0 * (double)((S + G - 1) / G);
-        if (p_group * groups_per_chunk <= 0.01) {
+        if (p_group * groups_per_chunk <= 0.02) {
             v.group = G;
             v.check = true;
             return v;
