@@ -595,6 +595,14 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
             const bool full_next = (!last_sub || tnext != kNoTile) && nsub < full_subs;
             if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, wn);
+            // ... and pull the one after that into L2, so that the register load above never waits on DRAM
+            if (kSub == 1 && p.l2_prefetch) {
+                const unsigned long long t2 = tile_of(p, k + 2u);
+                if (t2 != kNoTile && sub_index(t2, 0) < full_subs) {
+                    const uint32_t *a2 = in_lane + sub_index(t2, 0) * (unsigned long long)kSubWords;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a2));
+                }
+            }
 
             // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
             uint32_t los[NG], gss[NG];
