@@ -4,12 +4,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhuffb200.so")
+LIB_PATH = os.environ.get("HB_LIB") or os.path.join(_HERE, "libhuffb200.so")    # $HB_LIB: A/B builds
 
 HB_OK = 0
 HB_ERR_ARG, HB_ERR_CAPACITY, HB_ERR_CODELEN, HB_ERR_CODEWORD = -1, -2, -3, -4
 HB_ERR_CUDA, HB_ERR_NOMEM, HB_ERR_STATE = -5, -6, -7
-TILE_BYTES = 32768          # hb::kTileBytes (csrc/hb_kernels.cuh)
+
+TILE_BYTES = None           # hb::kTileBytes, filled in by load()
 
 u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
@@ -35,6 +36,7 @@ SIGNATURES = {
     "hb_stitch_seam": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
     "hb_synth_fill": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32p,
                                 C.c_int, u8p, vp]),
+    "hb_tile_bytes": (C.c_uint32, []),
     "hb_launch_count": (C.c_uint64, [vp]),
     "hb_encode_variant": (C.c_char_p, [u32p]),
     "hb_strerror": (C.c_char_p, [C.c_int]),
@@ -53,6 +55,8 @@ def load(path=LIB_PATH):
         fn = getattr(lib, name)          # AttributeError if the ABI and the header disagree
         fn.restype = res
         fn.argtypes = args
+    global TILE_BYTES
+    TILE_BYTES = int(lib.hb_tile_bytes())
     return lib
 
 

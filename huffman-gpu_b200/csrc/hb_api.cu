@@ -568,6 +568,8 @@ int hb_synth_fill(hb_ctx *ctx, uint8_t *d_out, uint64_t first, uint64_t n, uint6
     return HB_OK;
 }
 
+uint32_t hb_tile_bytes(void) { return (uint32_t)hb::kTileBytes; }
+
 uint64_t hb_launch_count(const hb_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 const char *hb_encode_variant(const uint32_t codewordlens[256])

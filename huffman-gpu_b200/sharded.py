@@ -21,8 +21,13 @@ import torch.distributed as dist
 from .encoder import bits_from_hist, build_codebook, shard_offsets
 
 
-def shard_bounds(n_words, world, tile_words=8192):
+def shard_bounds(n_words, world, tile_words=None):
     """Contiguous word ranges, boundaries on encode-tile multiples (last shard takes the ragged end)."""
+    if tile_words is None:
+        from . import capi
+        from .encoder import lib
+        lib()
+        tile_words = capi.TILE_BYTES // 4
     tiles = (n_words + tile_words - 1) // tile_words
     per = (tiles + world - 1) // world
     bounds = []

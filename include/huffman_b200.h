@@ -132,6 +132,9 @@ int hb_stitch_seam(hb_ctx *ctx, uint32_t *d_dst, const uint32_t *d_src, uint64_t
 int hb_synth_fill(hb_ctx *ctx, uint8_t *d_out, uint64_t first, uint64_t n, uint64_t seed, int mode,
                   int nbits, const uint32_t *thr, int K, const uint8_t *symmap, void *stream);
 
+/* Input bytes per encode tile (the unit of the look-back and of the work distribution): shard boundaries on
+ * multiples of it keep every shard's tiles full.  A property of the build, not of a context. */
+uint32_t hb_tile_bytes(void);
 /* Kernel launches issued through this context so far (bench.py's gpu_launches counter). */
 uint64_t hb_launch_count(const hb_ctx *ctx);
 /* Name of the encode kernel variant chosen for a codebook ("packed_g2", "wide_g1", ...). */

@@ -8,7 +8,7 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-TILE = 32768          # hb::kTileBytes: 16 worker warps x 2 KiB chunks (two 1 KiB sub-blocks)
+TILE = 32768          # about one encode tile (hb_tile_bytes(): worker warps x 2 KiB chunks)
 
 
 @pytest.fixture(scope="module")
@@ -413,4 +413,38 @@ def test_c4_fibonacci_sample_and_properties(hb, enc, orc, torch_mod):
         lo = w0 * 32 - start
         want = np.packbits(obits[lo:lo + (w1 - w0) * 32]).view(np.uint32).byteswap()
         assert np.array_equal(got, want)
+    big.close()
+
+
+def test_c5_8gib_properties(hb, orc, torch_mod):
+    """C5 (8 GiB, H~4.0): exact histogram mass, bit total = sum hist*len (the 64-bit oracle where
+    cpu_vlc_encode's uint32 outsize wraps), and oracle equality on random windows whose start bit is recomputed
+    from the prefix histogram.  Output offsets exceed 2^32 bits here (the reference's scan is uint32)."""
+    wl = hb.workloads.get("c5")
+    free, _ = torch_mod.cuda.mem_get_info()
+    if free < wl.n_bytes * 1.7:
+        pytest.skip("not enough device memory for the 8 GiB configuration")
+    big = hb.Encoder(device=0, max_bytes=wl.n_bytes)
+    d_in = synth_on_device(hb, big, torch_mod, wl)
+    hist = big.histogram(d_in)
+    assert int(hist.sum()) == wl.n_bytes
+    cw, cl, max_len = hb.build_codebook(hist)
+    bits_expected = hb.bits_from_hist(hist, cl)
+    assert bits_expected > 2 ** 32
+    d_out = torch_mod.empty(bits_expected // 32 + 2, dtype=torch_mod.int32, device="cuda")
+    assert big.encode(d_in, cw, cl, d_out) == bits_expected
+    rng = np.random.default_rng(5)
+    starts = [0, wl.n_bytes - 40 * TILE] + [int(x) * TILE for x in rng.integers(1, wl.n_bytes // TILE - 40, size=4)]
+    for a in starts:
+        b = a + 33 * TILE + 4 * int(rng.integers(0, 2048))
+        pre = big.histogram(d_in[:a]) if a else np.zeros(256, np.uint64)
+        start = hb.bits_from_hist(pre, cl)
+        window = d_in[a:b].cpu().numpy()
+        o_out, o_bits, _ = orc.encode(window.view(np.uint32), cw, cl)
+        w0, w1 = (start + 31) // 32, (start + o_bits) // 32           # fully covered global words
+        got = d_out[w0:w1].cpu().numpy().view(np.uint32)
+        obits = np.unpackbits(o_out.byteswap().view(np.uint8))
+        lo = w0 * 32 - start
+        want = np.packbits(obits[lo:lo + (w1 - w0) * 32]).view(np.uint32).byteswap()
+        assert np.array_equal(got, want), a
     big.close()

@@ -74,7 +74,8 @@ def test_sharded_plan_and_stitch_gloo(native_built, world, n_words):
 
 def test_shard_bounds():
     from huffman_gpu_b200 import sharded
-    b = sharded.shard_bounds(100000, 4)
-    assert b[0][0] == 0 and b[-1][1] == 100000
+    b = sharded.shard_bounds(1000000, 4)
+    assert b[0][0] == 0 and b[-1][1] == 1000000
     assert all(b[i][1] == b[i + 1][0] for i in range(3))
-    assert all(lo % 8192 == 0 for lo, hi in b if hi > lo)
+    from huffman_gpu_b200 import capi
+    assert all(lo % (capi.TILE_BYTES // 4) == 0 for lo, hi in b if hi > lo)
