@@ -419,6 +419,23 @@ def main():
             "bit_exact_vs_gpu": exact}
         if not exact:
             line["parity_error"] = "GPU stream differs from cpu_vlc_encode"
+    # ---- the reference's own 3-pass GPU pipeline on the same device buffer (N=1; inside its validity limits only) --
+    if rank == 0 and world == 1 and not args.no_cpu and args.workload in ("c1", "c2") and n_bytes % 16384 == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        rg = pyoracle.try_ref_gpu()
+        if rg is not None:
+            d_ref = torch.empty(n_bytes // 4, dtype=torch.int32, device="cuda")
+            rbits, ms_e, ms_s, ms_p = rg.run(d_in.data_ptr(), n_bytes // 4, cw, cl, d_ref.data_ptr(), n_bytes, repeats=5)
+            torch.cuda.synchronize()
+            nw = my_bits // 32
+            same = bool(rbits == my_bits and torch.equal(d_ref[:nw], d_out[:nw]))
+            line["reference_gpu"] = {
+                "what": "vlc_encode_kernel_sm64huff + prescanArray + cudaMemset + pack2 (unmodified kernels, sm_100a, "
+                        "oracle/ref_gpu_shim.cu), same device buffer",
+                "ms_encode": ms_e, "ms_scan": ms_s, "ms_memset_pack": ms_p, "ms_total": ms_e + ms_s + ms_p,
+                "value": n_bytes / ((ms_e + ms_s + ms_p) * 1e-3) / 1e9, "unit": UNIT, "bit_exact_vs_ours": same}
+            del d_ref
     if rank == 0:
         print(json.dumps(line))
     enc.close()

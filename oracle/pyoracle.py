@@ -144,6 +144,43 @@ class Ref:
         return rc, cw, cl
 
 
+class RefGpu:
+    """The unmodified reference GPU pipeline (encode -> scan -> memset + pack2) behind oracle/ref_gpu_shim.cu.
+    Valid only inside the reference's limits: 4 codewords <= 64 bits, <= 8192 bits per 1024-symbol block,
+    < 2^32 output bits, word count a multiple of 4096."""
+
+    def __init__(self):
+        path = os.path.join(_HERE, "_ref", "libref_gpu.so")
+        if not os.path.exists(path) and os.path.exists("/root/reference/pack_kernels.cu"):
+            build()
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        L = C.CDLL(path)
+        L.ref_gpu_pipeline.argtypes = [C.c_void_p, C.c_uint, _u32p, _u32p, C.c_void_p, C.c_uint64, _u32p,
+                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int]
+        L.ref_gpu_pipeline.restype = C.c_int
+        self.L = L
+
+    def run(self, d_in_ptr, n_words, cw, cl, d_packed_ptr, packed_bytes, repeats=1):
+        """-> (total_bits, ms_encode, ms_scan, ms_memset_pack); device pointers are plain integers"""
+        cw = np.ascontiguousarray(cw, dtype=np.uint32)
+        cl = np.ascontiguousarray(cl, dtype=np.uint32)
+        bits = C.c_uint32(0)
+        a, b, c = C.c_float(0), C.c_float(0), C.c_float(0)
+        rc = self.L.ref_gpu_pipeline(d_in_ptr, n_words, _ptr(cw, _u32p), _ptr(cl, _u32p), d_packed_ptr,
+                                     packed_bytes, C.byref(bits), C.byref(a), C.byref(b), C.byref(c), repeats)
+        if rc != 0:
+            raise RuntimeError("ref_gpu_pipeline failed: %d" % rc)
+        return int(bits.value), a.value, b.value, c.value
+
+
+def try_ref_gpu():
+    try:
+        return RefGpu()
+    except (FileNotFoundError, OSError):
+        return None
+
+
 def try_ref():
     try:
         return Ref()

@@ -448,3 +448,24 @@ def test_c5_8gib_properties(hb, orc, torch_mod):
         want = np.packbits(obits[lo:lo + (w1 - w0) * 32]).view(np.uint32).byteswap()
         assert np.array_equal(got, want), a
     big.close()
+
+
+def test_reference_gpu_pipeline_agrees_on_fixture(hb, enc, orc, torch_mod, c1):
+    """the reference's own 3-pass GPU path (unmodified kernels, oracle/ref_gpu_shim.cu), the
+    single-pass kernel and cpu_vlc_encode produce the same stream on the reference's fixture (config 1)."""
+    import pyoracle
+    rg = pyoracle.try_ref_gpu()
+    if rg is None:
+        pytest.skip("oracle/_ref/libref_gpu.so was not shipped")
+    data = hb.workloads.c1_fixture_bytes()
+    d_in = torch_mod.from_numpy(data.copy()).cuda()
+    d_ref = torch_mod.zeros(data.size // 4, dtype=torch_mod.int32, device="cuda")
+    bits, ms_enc, ms_scan, ms_pack = rg.run(d_in.data_ptr(), data.size // 4, c1["codewords"], c1["codewordlens"],
+                                            d_ref.data_ptr(), data.size)
+    torch_mod.cuda.synchronize()
+    assert bits == c1["total_bits"]
+    ours, our_bits = gpu_encode(enc, torch_mod, data, c1["codewords"], c1["codewordlens"])
+    nw = c1["n_words"]
+    ref_words = d_ref.cpu().numpy().view(np.uint32)[:nw]
+    assert our_bits == bits and np.array_equal(ref_words, ours[:nw])
+    assert orc.word_fnv(ref_words) == c1["fnv"]
