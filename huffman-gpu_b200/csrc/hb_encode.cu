@@ -58,6 +58,12 @@ namespace {
 constexpr int kW = kEncWorkers;
 constexpr int S = kSymPerThread;                        // symbols per lane per sub-block
 constexpr int kSub = kSubBlocks;
+// Input registers: double buffered (the next chunk lands while this one is encoded) or single buffered (the
+// next chunk is requested as soon as pass 1 has consumed this one; 16 fewer registers per thread).
+#ifndef HB_SINGLE_BUFFER
+#define HB_SINGLE_BUFFER 1
+#endif
+constexpr bool kSingleBuffer = HB_SINGLE_BUFFER != 0;
 constexpr int kLaneWords = S / 4;                        // input words per lane per sub-block
 constexpr int kSubWords = 32 * kLaneWords;               // input words per sub-block (one warp)
 static_assert(S % 32 == 0, "a lane reads whole 256-bit loads");
@@ -567,7 +573,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         return (t * (unsigned long long)kW + warp) * (unsigned long long)kSub + j;
     };
 
-    uint32_t w[kLaneWords], wn[kLaneWords];
+    uint32_t w[kLaneWords];
+    uint32_t wn[kLaneWords];                                  // unused (no registers) when single buffered
+    (void)wn;
     unsigned long long tile = tile_of(p, 0);
     bool full = tile != kNoTile && sub_index(tile, 0) < full_subs;
     if (full) ld_lane(in_lane + sub_index(tile, 0) * (unsigned long long)kSubWords, w);
@@ -587,14 +595,18 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             // filled `w` a sub-block ago are the same SASS instruction, so the first read of `w` would also
             // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old
             // (the registers are copied at the end of the loop, which is a read as well; this pins the order).
+            if constexpr (!kSingleBuffer) {
 #pragma unroll
-            for (int i = 0; i < kLaneWords; i += 8)                       // one register per load is enough
-                asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
+                for (int i = 0; i < kLaneWords; i += 8)                   // one register per load is enough
+                    asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
+            }
             long long t0 = prof.now();
             const bool last_sub = sub + 1u == (uint32_t)kSub;
             const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
             const bool full_next = (!last_sub || tnext != kNoTile) && nsub < full_subs;
-            if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, wn);
+            if constexpr (!kSingleBuffer) {
+                if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, wn);
+            }
             // ... and pull the one after that into L2, so that the register load above never waits on DRAM
             if (kSub == 1 && p.l2_prefetch) {
                 const unsigned long long t2 = tile_of(p, k + 2u);
@@ -644,6 +656,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
 #pragma unroll
                 for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
             }
+            // single buffered: pass 1 has consumed `w`; the next chunk has the rest of this tile to arrive
+            if constexpr (kSingleBuffer) {
+                if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, w);
+            }
             prof.add(kProfPass1, t0);
             t0 = prof.now();
 
@@ -668,9 +684,16 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                 if (CHECK && (ormask & ~31u)) {
                     // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one
                     // symbol at a time -- a single codeword (< 32 bits) always fits
+                    uint32_t wf[kLaneWords];
+                    if constexpr (kSingleBuffer) {                      // `w` already belongs to the next chunk
+                        ld_lane(in_lane + sub_index(tile, sub) * (unsigned long long)kSubWords, wf);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kLaneWords; i++) wf[i] = w[i];
+                    }
 #pragma unroll
                     for (int i = 0; i < S; i++) {
-                        const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
+                        const uint32_t off = __byte_perm(wf[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
                         const uint32_t cwl = tab_ld(off);
                         const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
                         const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
@@ -738,8 +761,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             prof.add(kProfEmit, t0);
 
             full = full_next;
+            if constexpr (!kSingleBuffer) {
 #pragma unroll
-            for (int i = 0; i < kLaneWords; i++) w[i] = wn[i];
+                for (int i = 0; i < kLaneWords; i++) w[i] = wn[i];
+            }
         }
 
         // ---------------- the chunk is staged: count, carry, hand-offs ----------------
