@@ -56,16 +56,9 @@ namespace hb {
 namespace {
 
 constexpr int kW = kEncWorkers;
-constexpr int S = kSymPerThread;                        // symbols per lane per sub-block
-constexpr int kSub = kSubBlocks;
-// Input registers: double buffered (the next chunk lands while this one is encoded) or single buffered (the
-// next chunk is requested as soon as pass 1 has consumed this one; 16 fewer registers per thread).
-#ifndef HB_SINGLE_BUFFER
-#define HB_SINGLE_BUFFER 1
-#endif
-constexpr bool kSingleBuffer = HB_SINGLE_BUFFER != 0;
-constexpr int kLaneWords = S / 4;                        // input words per lane per sub-block
-constexpr int kSubWords = 32 * kLaneWords;               // input words per sub-block (one warp)
+constexpr int S = kSymPerThread;                        // symbols per lane per chunk
+constexpr int kLaneWords = S / 4;                        // input words per lane per chunk
+constexpr int kChunkWords = 32 * kLaneWords;             // input words per chunk (one warp)
 static_assert(S % 32 == 0, "a lane reads whole 256-bit loads");
 constexpr int kPublisherWarp = kW;
 constexpr int kResolverWarp = kW + 1;
@@ -92,15 +85,14 @@ constexpr int kDepth = 8;                               // tiles a CTA may hold 
 constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
 constexpr uint32_t kRingBytes = kRingWords * 4;
 constexpr uint32_t kRingMask = kRingWords - 1;
-constexpr uint32_t kRingByteMask = kRingBytes - 1;
 constexpr int kRingsBelow = 7;                          // rings that fit under the table
 constexpr uint32_t kRingsBelowOffset = 0x2000 - kSmemReserved;
 constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
 constexpr uint32_t kCtrlOffset = 0;
 constexpr uint32_t kSmemBytes = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
 static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes == kTabOffset, "rings 0..6 end where the table starts");
-// a chunk is staged contiguously (mod ring size) and must fit even when every symbol takes the longest code
-static_assert((uint32_t)kSubBlocks * S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
+// a chunk is staged contiguously (it never wraps) and must fit even when every symbol takes the longest code
+static_assert((uint32_t)S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
 
 struct Ctrl {
     unsigned long long bar_sums[kDepth];        // workers -> publisher: chunk bit counts and carries of tile k posted
@@ -194,7 +186,7 @@ __device__ __forceinline__ void ld_lane(const uint32_t *p, uint32_t (&w)[kLaneWo
 #pragma unroll
     for (int i = 0; i < kLaneWords; i += 8) ld_stream_v8(p + i, w + i);
 }
-// ring access by shared-window byte address (rings are aligned to kRingBytes)
+// ring access by shared-window byte address
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
@@ -205,17 +197,6 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// address of ring position `pos` (an absolute word counter)
-__device__ __forceinline__ uint32_t ring_at(uint32_t ring_s, uint32_t pos)
-{
-    return ring_s | ((pos << 2) & kRingByteMask);
-}
-// advance a ring address by `bytes`, wrapping inside the ring
-__device__ __forceinline__ uint32_t ring_step(uint32_t ring_s, uint32_t addr, uint32_t bytes)
-{
-    return ring_s | ((addr + bytes) & kRingByteMask);
-}
-
 // ---- optional cycle accounting: build with -DHB_PROFILE and run with $HB_PROFILE=1 --------------------
 enum { kProfWaitTile = 0, kProfWaitPrefix, kProfWorker, kProfWaitSums, kProfWaitAgg, kProfLookback,
        kProfBitsBefore, kProfResolver, kProfTiles, kProfPolls, kProfPass1, kProfEmit, kProfCopy, kProfCount };
@@ -454,8 +435,8 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
 }
 
 // ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
-// `cnt` output words from a run of staged words that does not wrap: out[j] = the 32 bits that start `sh`
-// bits before staged word j; word 0 takes those leading bits from `first_before`.
+// `cnt` output words from a run of staged words: out[j] = the 32 bits that start `sh` bits before staged word j;
+// word 0 takes those leading bits from `first_before`.
 __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t cnt, uint32_t first_before,
                                          uint32_t sh, uint32_t lane)
 {
@@ -480,9 +461,9 @@ __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t
     }
 }
 
-// The chunk occupies ring positions start, start+1, ... (mod kRingWords); `ring_s` is the ring's window address.
-__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, uint32_t ring_s, uint32_t start,
-                                         uint32_t k, uint32_t n, uint32_t warp, uint32_t lane)
+// The chunk occupies the staged words at window address `st_s` onwards (contiguous: chunks never wrap).
+__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, uint32_t st_s, uint32_t k, uint32_t n,
+                                         uint32_t warp, uint32_t lane)
 {
     const uint32_t slot = slot_of(k);
     // the (< 32) bits that precede this chunk: neighbours' carries, then the tile's `prev`
@@ -500,20 +481,15 @@ __device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, uint32_
     const uint32_t nfull = (uint32_t)((end >> 5) - g0);        // words whose last bit is ours (<= ceil(n/32))
     const bool last = ctrl->flags[slot] && warp == (uint32_t)kW - 1;   // the job's final word(s)
     if (!last && g0 + nfull <= p.out_cap_words) {
-        // common case: every word this chunk owns comes from two neighbouring staged words; the staged run
-        // wraps around the ring at most once
-        uint32_t *out = p.out + g0;
-        const uint32_t s0 = start & kRingMask;
-        const uint32_t run0 = min(nfull, kRingWords - s0);
-        copy_run(out, ring_s + s0 * 4u, run0, cin, sh, lane);
-        if (run0 < nfull) copy_run(out + run0, ring_s, nfull - run0, lds_u32(ring_s + kRingBytes - 4u), sh, lane);
+        // common case: every word this chunk owns comes from two neighbouring staged words
+        copy_run(p.out + g0, st_s, nfull, cin, sh, lane);
     } else {
         const uint32_t nwrite = nfull + (last ? 1u : 0u);
         const uint32_t nstage = (n + 31u) >> 5;
         bool spill = false;
         for (uint32_t j = lane; j < nwrite; j += 32u) {
-            const uint32_t cur = (j < nstage) ? lds_u32(ring_at(ring_s, start + j)) : 0u;
-            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? lds_u32(ring_at(ring_s, start + j - 1u)) : 0u);
+            const uint32_t cur = (j < nstage) ? lds_u32(st_s + 4u * j) : 0u;
+            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? lds_u32(st_s + 4u * j - 4u) : 0u);
             const uint32_t v = __funnelshift_r(cur, before, sh);
             if (g0 + j < p.out_cap_words)
                 p.out[g0 + j] = v;
@@ -545,8 +521,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
 
-    // ---- the staging ring: chunks [retired, emitted) of this worker, then the chunk being encoded, occupy ring
-    //      positions [tail, head + words so far); positions are absolute counters, the index is position mod size
+    // ---- the staging ring: the chunks [retired, emitted) of this worker occupy ring positions [tail, head);
+    //      positions are absolute word counters, the index is position mod size; a chunk never wraps (the
+    //      words up to the end of the ring are skipped instead)
     uint32_t emitted = 0, retired = 0, head = 0, tail = 0;
     auto retire = [&](bool blocking) {
         const uint32_t k = retired, slot = slot_of(k);
@@ -558,224 +535,179 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         }
         const long long t0 = prof.now();
         const uint2 ch = ctrl->chunk[warp][slot];
-        copy_out(p, ctrl, ring_s, ch.x, k, ch.y, warp, lane);
+        copy_out(p, ctrl, ring_s + (ch.x & kRingMask) * 4u, k, ch.y, warp, lane);
         retired++;
         tail = (retired < emitted) ? ctrl->chunk[warp][slot_of(retired)].x : head;
         __syncwarp();
         prof.add(kProfCopy, t0);
     };
 
-    // sub-block j (0 .. kSub-1) of this warp's chunk of tile t is global sub-block (t * kW + warp) * kSub + j,
-    // kSubWords words each; a sub-block is `full` when it lies entirely inside the input
-    const unsigned long long full_subs = p.n_words / (unsigned long long)kSubWords;   // indices below this are full
+    // this warp's chunk of tile t is chunk t * kW + warp of the input, kChunkWords words; it is `full` when it
+    // lies entirely inside the input
+    const unsigned long long full_chunks = p.n_words / (unsigned long long)kChunkWords;
     const uint32_t *in_lane = p.in + lane * (uint32_t)kLaneWords;
-    auto sub_index = [&](unsigned long long t, uint32_t j) {
-        return (t * (unsigned long long)kW + warp) * (unsigned long long)kSub + j;
-    };
+    auto chunk_index = [&](unsigned long long t) { return t * (unsigned long long)kW + warp; };
 
     uint32_t w[kLaneWords];
-    uint32_t wn[kLaneWords];                                  // unused (no registers) when single buffered
-    (void)wn;
     unsigned long long tile = tile_of(p, 0);
-    bool full = tile != kNoTile && sub_index(tile, 0) < full_subs;
-    if (full) ld_lane(in_lane + sub_index(tile, 0) * (unsigned long long)kSubWords, w);
+    bool full = tile != kNoTile && chunk_index(tile) < full_chunks;
+    if (full) ld_lane(in_lane + chunk_index(tile) * (unsigned long long)kChunkWords, w);
 
     for (; tile != kNoTile;) {
         const uint32_t k = emitted, slot = slot_of(k);
         // slot k % kDepth still belongs to tile k - kDepth until that one has been copied out
         if (emitted - retired >= (uint32_t)kDepth) retire(true);
         const unsigned long long tnext = tile_of(p, k + 1u);
+        const bool full_next = tnext != kNoTile && chunk_index(tnext) < full_chunks;
+        long long t0 = prof.now();
 
-        uint32_t qbase = 0;                                    // bits of this chunk emitted so far
-        uint32_t prev_tail = 0;                                // the partial word that ends at qbase (left-aligned)
-#pragma unroll 1
-        for (uint32_t sub = 0; sub < (uint32_t)kSub; sub++) {
-            // ---------------- prefetch the next sub-block ----------------
-            // Scoreboard slots count per instruction, not per register: the load below and the one that
-            // filled `w` a sub-block ago are the same SASS instruction, so the first read of `w` would also
-            // wait for the NEW load.  Reading `w` here, before the new load is issued, only waits for the old
-            // (the registers are copied at the end of the loop, which is a read as well; this pins the order).
-            if constexpr (!kSingleBuffer) {
+        // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
+        uint32_t los[NG], gss[NG];
+        uint32_t bt = 0, ormask = 0;
+        if (full) {
+            uint32_t lo = 0, gs = 0;
 #pragma unroll
-                for (int i = 0; i < kLaneWords; i += 8)                   // one register per load is enough
-                    asm volatile("prmt.b32 %0, %0, 0, 0x3210;" : "+r"(w[i]));
-            }
-            long long t0 = prof.now();
-            const bool last_sub = sub + 1u == (uint32_t)kSub;
-            const unsigned long long nsub = last_sub ? sub_index(tnext, 0) : sub_index(tile, sub + 1u);
-            const bool full_next = (!last_sub || tnext != kNoTile) && nsub < full_subs;
-            if constexpr (!kSingleBuffer) {
-                if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, wn);
-            }
-            // ... and pull the one after that into L2, so that the register load above never waits on DRAM
-            if (kSub == 1 && p.l2_prefetch) {
-                const unsigned long long t2 = tile_of(p, k + 2u);
-                if (t2 != kNoTile && sub_index(t2, 0) < full_subs) {
-                    const uint32_t *a2 = in_lane + sub_index(t2, 0) * (unsigned long long)kSubWords;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a2));
-                }
-            }
-
-            // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
-            uint32_t los[NG], gss[NG];
-            uint32_t bt = 0, ormask = 0;
-            if (full) {
-                uint32_t lo = 0, gs = 0;
-#pragma unroll
-                for (int i = 0; i < S; i++) {
-                    // {lane*4, symbol, table address bytes 2..3}: the whole lookup address in one prmt
-                    const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
-                    if (WIDE) {
-                        const uint32_t cwl = tab_ld(off);
-                        const uint32_t l = tab_ld_len(off);
-                        lo = __funnelshift_l(cwl, lo, l);
-                        gs += l;
-                    } else {
-                        const uint32_t e = tab_ld(off);
-                        lo = __funnelshift_l(e, lo, e);       // (lo << len) | cw, len = e & 31
-                        gs = __dp4a(e, 1u, gs);               // + (e & 0xFF)
-                    }
-                    if ((i % G) == G - 1 || i == S - 1) {
-                        los[i / G] = lo;
-                        gss[i / G] = gs;
-                        bt += gs;
-                        if (CHECK) ormask |= gs;
-                        gs = 0;
-                    }
-                }
-            } else {
-                const unsigned long long sym0 = sub_index(tile, sub) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
-#pragma unroll 1
-                for (int i = 0; i < S; i++) {
-                    if (sym0 + i < n_bytes) {
-                        uint32_t cwl, l;
-                        fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
-                        bt += l;
-                    }
-                }
-#pragma unroll
-                for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
-            }
-            // single buffered: pass 1 has consumed `w`; the next chunk has the rest of this tile to arrive
-            if constexpr (kSingleBuffer) {
-                if (full_next) ld_lane(in_lane + nsub * (unsigned long long)kSubWords, w);
-            }
-            prof.add(kProfPass1, t0);
-            t0 = prof.now();
-
-            // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
-            uint32_t incl = bt;
-#pragma unroll
-            for (int i = 0; i < 5; i++) incl += __shfl_up_sync(0xFFFFFFFFu, incl, 1u << i) * scan_on[i];
-            const uint32_t q0 = qbase + incl - bt;
-            const uint32_t qend = qbase + __shfl_sync(0xFFFFFFFFu, incl, 31);
-
-            // ---------------- room in the ring for the chunk so far (older chunks leave first) ----------------
-            while (head + (qend >> 5) + 2u - tail > kRingWords) retire(true);
-
-            // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
-            // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
-            const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
-            if (fast) {
-                uint32_t r = q0 & 31u;                        // bits already in the word being filled
-                const uint32_t wa0 = ring_at(ring_s, head + (q0 >> 5));
-                uint32_t wa = wa0;                            // that word's address
-                uint32_t lo_prev = 0;
-                if (CHECK && (ormask & ~31u)) {
-                    // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one
-                    // symbol at a time -- a single codeword (< 32 bits) always fits
-                    uint32_t wf[kLaneWords];
-                    if constexpr (kSingleBuffer) {                      // `w` already belongs to the next chunk
-                        ld_lane(in_lane + sub_index(tile, sub) * (unsigned long long)kSubWords, wf);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kLaneWords; i++) wf[i] = w[i];
-                    }
-#pragma unroll
-                    for (int i = 0; i < S; i++) {
-                        const uint32_t off = __byte_perm(wf[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
-                        const uint32_t cwl = tab_ld(off);
-                        const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
-                        const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
-                        r += l;
-                        if (r >= 32u) {
-                            sts_u32(wa, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), r));
-                            wa = ring_step(ring_s, wa, 4u);
-                            r -= 32u;
-                        }
-                        lo_prev = lo_new;
-                    }
+            for (int i = 0; i < S; i++) {
+                // {lane*4, symbol, table address bytes 2..3}: the whole lookup address in one prmt
+                const uint32_t off = __byte_perm(w[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
+                if (WIDE) {
+                    const uint32_t cwl = tab_ld(off);
+                    const uint32_t l = tab_ld_len(off);
+                    lo = __funnelshift_l(cwl, lo, l);
+                    gs += l;
                 } else {
-#pragma unroll
-                    for (int g = 0; g < NG; g++) {
-                        r += gss[g];
-                        if (r >= 32u) {
-                            // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
-                            // before this group, the rest from the window after it (funnel shifts use r mod 32)
-                            const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                            sts_u32(wa, __funnelshift_r(los[g], hi, r));
-                            wa = ring_step(ring_s, wa, 4u);
-                            r -= 32u;
-                        }
-                        lo_prev = los[g];
-                    }
+                    const uint32_t e = tab_ld(off);
+                    lo = __funnelshift_l(e, lo, e);           // (lo << len) | cw, len = e & 31
+                    gs = __dp4a(e, 1u, gs);                   // + (e & 0xFF)
                 }
-                const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
-                uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
-                if (lane == 0) left_tail = prev_tail;         // the previous sub-block's last partial word
-                if (q0 & 31u) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
-                prev_tail = __shfl_sync(0xFFFFFFFFu, tailw, 31);
-                if (lane == 31 && r) sts_u32(wa, tailw);      // wa == the word that holds bit qend
-            } else {
-                const unsigned long long sym0 = sub_index(tile, sub) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
-                // words that begin inside this sub-block start from zero; the word shared with the previous
-                // sub-block already holds its bits
-                for (uint32_t j = ((qbase + 31u) >> 5) + lane; j < ((qend + 31u) >> 5); j += 32u)
-                    sts_u32(ring_at(ring_s, head + j), 0u);
-                __syncwarp();
-                uint32_t *ring = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(ring_s));
-                uint32_t q = q0, lo = 0;
+                if ((i % G) == G - 1 || i == S - 1) {
+                    los[i / G] = lo;
+                    gss[i / G] = gs;
+                    bt += gs;
+                    if (CHECK) ormask |= gs;
+                    gs = 0;
+                }
+            }
+        } else {
+            const unsigned long long sym0 = chunk_index(tile) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
 #pragma unroll 1
+            for (int i = 0; i < S; i++) {
+                if (sym0 + i < n_bytes) {
+                    uint32_t cwl, l;
+                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
+                    bt += l;
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
+        }
+        // Pass 1 has consumed `w`: request the next chunk now; it has the rest of this tile to arrive.  (One set
+        // of input registers instead of two: measured +5-7 %, and no scoreboard aliasing between the two loads.)
+        if (full_next) ld_lane(in_lane + chunk_index(tnext) * (unsigned long long)kChunkWords, w);
+        if (p.l2_prefetch) {
+            const unsigned long long t2 = tile_of(p, k + 2u);
+            if (t2 != kNoTile && chunk_index(t2) < full_chunks)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_lane + chunk_index(t2) * (unsigned long long)kChunkWords));
+        }
+        prof.add(kProfPass1, t0);
+        t0 = prof.now();
+
+        // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
+        uint32_t incl = bt;
+#pragma unroll
+        for (int i = 0; i < 5; i++) incl += __shfl_up_sync(0xFFFFFFFFu, incl, 1u << i) * scan_on[i];
+        const uint32_t q0 = incl - bt;
+        const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
+
+        // ---------------- room in the ring: contiguous, older chunks leave first if it is full ----------------
+        const uint32_t need = n ? ((n + 31u) >> 5) : 1u;
+        if ((head & kRingMask) + need > kRingWords) head = (head | kRingMask) + 1u;   // skip to the ring start
+        if (emitted == retired) tail = head;                   // nothing staged: the ring is empty wherever we are
+        while (head + need - tail > kRingWords) retire(true);
+        const uint32_t st_s = ring_s + (head & kRingMask) * 4u;    // window address of the chunk's first word
+
+        // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
+        // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
+        const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
+        if (fast) {
+            uint32_t r = q0 & 31u;                            // bits already in the word being filled
+            const uint32_t wa0 = st_s + (q0 >> 5) * 4u;
+            uint32_t wa = wa0;                                // that word's address
+            uint32_t lo_prev = 0;
+            if (CHECK && (ormask & ~31u)) {
+                // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one
+                // symbol at a time -- a single codeword (< 32 bits) always fits.  `w` already belongs to the next
+                // chunk, so the lane's symbols are read again.
+                uint32_t wf[kLaneWords];
+                ld_lane(in_lane + chunk_index(tile) * (unsigned long long)kChunkWords, wf);
+#pragma unroll
                 for (int i = 0; i < S; i++) {
-                    if (sym0 + i < n_bytes) {
-                        uint32_t cwl, l;
-                        fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
-                        if (l) {
-                            const uint32_t ln = __funnelshift_l(cwl, lo, l);
-                            const uint32_t qn = q + l;
-                            if ((qn ^ q) & ~31u)
-                                atomicOr(&ring[(head + (qn >> 5) - 1u) & kRingMask],
-                                         __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
-                            q = qn;
-                            lo = ln;
-                        }
+                    const uint32_t off = __byte_perm(wf[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
+                    const uint32_t cwl = tab_ld(off);
+                    const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
+                    const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
+                    r += l;
+                    if (r >= 32u) {
+                        sts_u32(wa, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), r));
+                        wa += 4u;
+                        r -= 32u;
+                    }
+                    lo_prev = lo_new;
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    r += gss[g];
+                    if (r >= 32u) {
+                        // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
+                        // before this group, the rest from the window after it (funnel shifts use r mod 32)
+                        const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
+                        sts_u32(wa, __funnelshift_r(los[g], hi, r));
+                        wa += 4u;
+                        r -= 32u;
+                    }
+                    lo_prev = los[g];
+                }
+            }
+            const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
+            const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
+            if (lane != 0 && (q0 & 31u)) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
+            if (lane == 31 && r) sts_u32(wa, tailw);          // wa == the word that holds bit n
+        } else {
+            const unsigned long long sym0 = chunk_index(tile) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
+            for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) sts_u32(st_s + 4u * j, 0u);
+            __syncwarp();
+            uint32_t *st = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(st_s));
+            uint32_t q = q0, lo = 0;
+#pragma unroll 1
+            for (int i = 0; i < S; i++) {
+                if (sym0 + i < n_bytes) {
+                    uint32_t cwl, l;
+                    fetch_entry<WIDE>(tab_s, bytes[byte_of_symbol(sym0 + i)], lane, cwl, l);
+                    if (l) {
+                        const uint32_t ln = __funnelshift_l(cwl, lo, l);
+                        const uint32_t qn = q + l;
+                        if ((qn ^ q) & ~31u)
+                            atomicOr(&st[(qn >> 5) - 1u], __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
+                        q = qn;
+                        lo = ln;
                     }
                 }
-                const uint32_t f = q & 31u;
-                if (f) atomicOr(&ring[(head + (q >> 5)) & kRingMask], lo << (32u - f));
-                __syncwarp();
-                prev_tail = (qend & 31u) ? lds_u32(ring_at(ring_s, head + (qend >> 5))) : 0u;
             }
-            qbase = qend;
-            __syncwarp();                                     // orders this sub-block's ring writes before the next one's
-            prof.add(kProfEmit, t0);
-
-            full = full_next;
-            if constexpr (!kSingleBuffer) {
-#pragma unroll
-                for (int i = 0; i < kLaneWords; i++) w[i] = wn[i];
-            }
+            const uint32_t f = q & 31u;
+            if (f) atomicOr(&st[q >> 5], lo << (32u - f));
         }
+        __syncwarp();
+        prof.add(kProfEmit, t0);
 
         // ---------------- the chunk is staged: count, carry, hand-offs ----------------
-        const uint32_t n = qbase;
         if (lane == 0) {
             // carry: the last (<= 31) bits of this chunk, for the right-hand neighbour
             uint32_t val = 0;
             if (n) {
                 const uint32_t a = (n - 1u) >> 5, r = n & 31u;
-                const uint32_t w1 = lds_u32(ring_at(ring_s, head + a));
-                const uint32_t w0 = a ? lds_u32(ring_at(ring_s, head + a - 1u)) : 0u;
+                const uint32_t w1 = lds_u32(st_s + 4u * a);
+                const uint32_t w0 = a ? lds_u32(st_s + 4u * a - 4u) : 0u;
                 val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
             }
             ctrl->carry_val[k & 15u][warp] = val;
@@ -784,7 +716,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             ctrl->sums[slot][warp] = n;
             mbar_arrive(&ctrl->bar_sums[slot]);
         }
-        head += n ? ((n + 31u) >> 5) : 1u;
+        head += need;
         emitted++;
         __syncwarp();
 
@@ -793,6 +725,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             retire(false);
 
         tile = tnext;
+        full = full_next;
     }
     while (retired < emitted) retire(true);
     prof.add(kProfWorker, t_worker);

@@ -14,9 +14,8 @@ namespace hb {
 // work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
 constexpr int kEncWorkers = 16;
 constexpr int kEncThreads = (kEncWorkers + 3) * 32;
-constexpr int kSymPerThread = 64;                                     // symbols (bytes) per lane per sub-block
-constexpr int kSubBlocks = 1;                                         // sub-blocks per chunk
-constexpr int kChunkBytes = kSubBlocks * 32 * kSymPerThread;          // one warp: 2 KiB
+constexpr int kSymPerThread = 64;                                     // symbols (bytes) per lane per chunk
+constexpr int kChunkBytes = 32 * kSymPerThread;                       // one warp: 2 KiB
 constexpr int kTileBytes = kEncWorkers * kChunkBytes;                 // 32 KiB
 constexpr int kTileWords = kTileBytes / 4;
 
