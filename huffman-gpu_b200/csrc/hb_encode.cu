@@ -193,6 +193,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
+// the same load without ordering constraints: for phases that only read staged words (lets the compiler batch)
+__device__ __forceinline__ uint32_t lds_free(uint32_t addr)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
@@ -440,24 +447,20 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
 __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t cnt, uint32_t first_before,
                                          uint32_t sh, uint32_t lane)
 {
+    // two words per lane per trip, every trip independent of the others (loads first, then stores)
     uint32_t a = src_s + lane * 4u;
     uint32_t *o = out + lane;
-    uint32_t j = lane;
-    if (j < cnt) {                                             // peeled: only word 0 lacks a staged predecessor
-        const uint32_t before = j ? lds_u32(a - 4u) : first_before;
-        *o = __funnelshift_r(lds_u32(a), before, sh);
-    }
-    for (j += 32u; j + 32u < cnt; j += 64u) {                  // two words per lane per trip
-        a += 256u;
-        o += 64;
-        const uint32_t c0 = lds_u32(a - 128u), b0 = lds_u32(a - 132u);
-        const uint32_t c1 = lds_u32(a), b1 = lds_u32(a - 4u);
-        o[-32] = __funnelshift_r(c0, b0, sh);
-        o[0] = __funnelshift_r(c1, b1, sh);
-    }
-    if (j < cnt) {
-        a += 128u;
-        o[32] = __funnelshift_r(lds_u32(a), lds_u32(a - 4u), sh);
+    for (uint32_t j = lane; j < cnt; j += 64u, a += 256u, o += 64) {
+        const bool two = j + 32u < cnt;
+        const uint32_t c0 = lds_free(a);
+        const uint32_t b0 = j ? lds_free(a - 4u) : first_before;       // only word 0 lacks a staged predecessor
+        uint32_t c1 = 0, b1 = 0;
+        if (two) {
+            c1 = lds_free(a + 128u);
+            b1 = lds_free(a + 124u);
+        }
+        o[0] = __funnelshift_r(c0, b0, sh);
+        if (two) o[32] = __funnelshift_r(c1, b1, sh);
     }
 }
 
@@ -630,9 +633,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
         const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
         if (fast) {
-            uint32_t r = q0 & 31u;                            // bits already in the word being filled
-            const uint32_t wa0 = st_s + (q0 >> 5) * 4u;
-            uint32_t wa = wa0;                                // that word's address
+            const uint32_t wa0 = st_s + (q0 >> 5) * 4u;       // the word this lane starts in
+            uint32_t q = q0;                                  // chunk-relative bit position (the only serial chain)
             uint32_t lo_prev = 0;
             if (CHECK && (ormask & ~31u)) {
                 // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one
@@ -646,15 +648,15 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                     const uint32_t cwl = tab_ld(off);
                     const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
                     const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
-                    r += l;
-                    if (r >= 32u) {
-                        sts_u32(wa, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), r));
-                        wa += 4u;
-                        r -= 32u;
-                    }
+                    const uint32_t qn = q + l;
+                    if ((qn ^ q) >= 32u)
+                        sts_u32(st_s + (q >> 5) * 4u, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+                    q = qn;
                     lo_prev = lo_new;
                 }
             } else {
+                uint32_t r = q0 & 31u;                        // bits already in the word being filled
+                uint32_t wa = wa0;                            // that word's address
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
                     r += gss[g];
@@ -666,13 +668,15 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                         wa += 4u;
                         r -= 32u;
                     }
+                    q += gss[g];
                     lo_prev = los[g];
                 }
             }
+            const uint32_t r = q & 31u;
             const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
             const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
             if (lane != 0 && (q0 & 31u)) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
-            if (lane == 31 && r) sts_u32(wa, tailw);          // wa == the word that holds bit n
+            if (lane == 31 && r) sts_u32(st_s + (q >> 5) * 4u, tailw);             // the word that holds bit n
         } else {
             const unsigned long long sym0 = chunk_index(tile) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
             for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) sts_u32(st_s + 4u * j, 0u);
