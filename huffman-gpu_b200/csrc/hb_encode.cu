@@ -64,7 +64,6 @@ constexpr int kPublisherWarp = kW;
 constexpr int kResolverWarp = kW + 1;
 constexpr int kSlotStride = 256;                        // table stride per symbol (bytes)
 constexpr int kTabBytes = 256 * kSlotStride;            // 64 KiB
-constexpr unsigned long long kNoTile = ~0ULL;
 // Fenwick node = [63:44] tiles counted | [43:0] bits summed
 constexpr int kTreeCountShift = 44;
 constexpr unsigned long long kTreeOne = 1ULL << kTreeCountShift;
@@ -94,31 +93,34 @@ static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes == kTabOffset, "rings
 // a chunk is staged contiguously (it never wraps) and must fit even when every symbol takes the longest code
 static_assert((uint32_t)S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
 
-struct Ctrl {
-    unsigned long long bar_sums[kDepth];        // workers -> publisher: chunk bit counts and carries of tile k posted
-    unsigned long long bar_agg[kDepth];         // publisher -> resolver: aggregate of tile k published
-    unsigned long long bar_prefix[kDepth];      // resolver -> workers: global offset of tile k resolved
-    unsigned long long prefix[kDepth];
-    uint32_t prev[kDepth];
-    uint32_t flags[kDepth];
-    uint32_t btile[kDepth];
-    uint32_t woff[kDepth][kW];
-    uint32_t sums[kDepth][kW];
-    uint32_t carry_val[16][kW];
-    uint32_t carry_cnt[16][kW];
-    uint2 chunk[kW][kDepth];                    // worker-private: {ring position, bits} of its staged chunks
-};
 
+// Control block at the start of the dynamic block.  Everything in it is addressed through the shared WINDOW
+// (plain ld/st.shared on 32-bit addresses): generic pointers cost a conversion on every access.
+struct Ctrl {
+    unsigned long long bar_sums[kDepth];        // workers -> publisher: the 16 chunks of tile k are staged
+    unsigned long long bar_agg[kDepth];         // publisher -> resolver: aggregate of tile k published
+    unsigned long long bar_prefix[kDepth];      // resolver -> workers: copy-out records of tile k posted
+    uint2 chunk[kDepth][kW];                    // worker w, tile k: {ring position, bits} of its staged chunk
+    uint4 rec[kDepth][kW];                      // resolver -> worker w: {out word index lo, hi, carry-in, sh | flags}
+};
 static_assert(sizeof(Ctrl) <= kRingsBelowOffset, "the control block must fit below the first ring");
+constexpr uint32_t kCtrlS = kSmemReserved + kCtrlOffset;
+constexpr uint32_t kBarSumsS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_sums);
+constexpr uint32_t kBarAggS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_agg);
+constexpr uint32_t kBarPrefixS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_prefix);
+constexpr uint32_t kChunkS = kCtrlS + (uint32_t)offsetof(Ctrl, chunk);
+constexpr uint32_t kRecS = kCtrlS + (uint32_t)offsetof(Ctrl, rec);
+constexpr uint32_t kRecSlow = 0x100u;                   // record flags: leave the fast copy-out
+constexpr uint32_t kRecLast = 0x200u;                   // the job's final chunk (partial word, courtesy zero word)
 
 // position k of a CTA's tile sequence -> slot k % kDepth and mbarrier parity (k / kDepth) & 1
 __device__ __forceinline__ uint32_t slot_of(uint32_t k) { return k & (uint32_t)(kDepth - 1); }
 __device__ __forceinline__ uint32_t par_of(uint32_t k) { return (k / (uint32_t)kDepth) & 1u; }
-// the k-th tile of this CTA (static interleave: the tiles in flight across the grid are consecutive)
-__device__ __forceinline__ unsigned long long tile_of(const EncParams &p, uint32_t k)
+// window address of worker w's staging ring
+__device__ __forceinline__ uint32_t ring_window(uint32_t w)
 {
-    const unsigned long long t = p.first_tile + (unsigned long long)k * gridDim.x + blockIdx.x;
-    return t < p.end_tile ? t : kNoTile;
+    return w < (uint32_t)kRingsBelow ? kSmemReserved + kRingsBelowOffset + w * kRingBytes
+                                     : kSmemReserved + kRingsAboveOffset + (w - (uint32_t)kRingsBelow) * kRingBytes;
 }
 
 // ---- small PTX helpers --------------------------------------------------------------------------
@@ -126,17 +128,16 @@ __device__ __forceinline__ uint32_t smem_addr(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar_s, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_s)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity)
 {
-    const uint32_t a = smem_addr(bar);
     for (;;) {
         uint32_t done;
         asm volatile(
@@ -144,13 +145,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(a), "r"(parity)
+            : "r"(bar_s), "r"(parity)
             : "memory");
         if (done) break;
         __nanosleep(200);               // a blocked warp must not compete for issue slots
     }
 }
-__device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_test(uint32_t bar_s, uint32_t parity)
 {
     uint32_t done;
     asm volatile(
@@ -158,7 +159,7 @@ __device__ __forceinline__ bool mbar_test(unsigned long long *bar, uint32_t pari
         "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(smem_addr(bar)), "r"(parity)
+        : "r"(bar_s), "r"(parity)
         : "memory");
     return done != 0;
 }
@@ -180,17 +181,32 @@ __device__ __forceinline__ void ld_stream_v8(const uint32_t *p, uint32_t *w)
                    "=r"(w[7])
                  : "l"(p));
 }
-// a lane's S contiguous symbols of one sub-block
+// a lane's S contiguous symbols of one chunk
 __device__ __forceinline__ void ld_lane(const uint32_t *p, uint32_t (&w)[kLaneWords])
 {
 #pragma unroll
     for (int i = 0; i < kLaneWords; i += 8) ld_stream_v8(p + i, w + i);
 }
-// ring access by shared-window byte address
+// shared memory by window address
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr)
+                 : "memory");
     return v;
 }
 // the same load without ordering constraints: for phases that only read staged words (lets the compiler batch)
@@ -203,6 +219,14 @@ __device__ __forceinline__ uint32_t lds_free(uint32_t addr)
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 // ---- optional cycle accounting: build with -DHB_PROFILE and run with $HB_PROFILE=1 --------------------
 enum { kProfWaitTile = 0, kProfWaitPrefix, kProfWorker, kProfWaitSums, kProfWaitAgg, kProfLookback,
@@ -316,24 +340,14 @@ __device__ uint32_t bits_before(const EncParams &p, uint32_t tab_s, unsigned lon
 // ---- publisher warp: tile aggregates -----------------------------------------------------------------------
 // Never waits on another CTA: as soon as the 16 chunk counts of a tile are in, their sum goes into the
 // tree, whatever state this CTA's own look-backs are in.
-__device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
+__device__ void publisher(const EncParams &p, uint32_t lane, uint32_t K)
 {
-    for (uint32_t k = 0;; k++) {
+    unsigned long long t_cur = p.first_tile + blockIdx.x;
+    for (uint32_t k = 0; k < K; k++, t_cur += gridDim.x) {
         const uint32_t slot = slot_of(k);
-        const unsigned long long t_cur = tile_of(p, k);
-        if (t_cur == kNoTile) break;
-        mbar_wait(&ctrl->bar_sums[slot], par_of(k));
-
-        // exclusive scan of the 16 chunk bit counts
-        const uint32_t n = (lane < (uint32_t)kW) ? ctrl->sums[slot][lane] : 0u;
-        uint32_t incl = n;
-#pragma unroll
-        for (int d = 1; d < kW; d <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-            if (lane >= (uint32_t)d) incl += v;
-        }
-        const uint32_t btile = __shfl_sync(0xFFFFFFFFu, incl, kW - 1);
-        if (lane < (uint32_t)kW) ctrl->woff[slot][lane] = incl - n;
+        mbar_wait(kBarSumsS + slot * 8u, par_of(k));
+        const uint32_t n = (lane < (uint32_t)kW) ? lds_u32(kChunkS + (slot * kW + lane) * 8u + 4u) : 0u;
+        const uint32_t btile = __reduce_add_sync(0xFFFFFFFFu, n);
         // Fenwick update: lane j adds {1 tile, btile bits} to the j-th node above tile t_cur (1-based index
         // t_cur + 1, then repeatedly + lowbit).  Nodes at or beyond the last tile are never read: skip them.
         {
@@ -342,38 +356,41 @@ __device__ void publisher(const EncParams &p, Ctrl *ctrl, uint32_t lane)
             if (i < p.n_tiles) red_add_u64(&p.tree[i], kTreeOne | (unsigned long long)btile);
         }
         __syncwarp();
-        if (lane == 0) {
-            ctrl->btile[slot] = btile;
-            mbar_arrive(&ctrl->bar_agg[slot]);
-        }
+        if (lane == 0) mbar_arrive(kBarAggS + slot * 8u);
     }
 }
 
-// ---- resolver warp: look-back over the Fenwick tree --------------------------------------------------------
+// ---- resolver warp: look-back over the Fenwick tree, then the copy-out records of the tile's 16 chunks --------
 // Two resolver warps share the CTA's tile sequence: resolver r takes positions r, r + 2, r + 4, ...
+// Everything a worker needs to copy its chunk out is computed here, 16 chunks in 16 lanes: the chunk's global
+// bit offset (look-back result + scan of the 16 counts), hence its first output word and phase, and the (< 32)
+// stream bits that precede it, taken from the left neighbours' staged words (or, for chunk 0, re-derived from
+// the 32 symbols before the tile: no inter-CTA data dependency).
 template <bool WIDE>
-__device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_t lane, uint32_t first)
+__device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint32_t first, uint32_t K)
 {
     Prof prof(p, first == 0);
     const long long t_all = prof.now();
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
-    // the symbol `lane + 1` places before a tile, for the (< 32) stream bits that precede it
-    auto tail_symbol = [&](unsigned long long t) -> uint32_t {
-        if (t == kNoTile) return 0u;
+    const unsigned long long tile0 = p.first_tile + blockIdx.x;
+    // the symbol `lane + 1` places before the k-th tile, for the (< 32) stream bits that precede it
+    auto tail_symbol = [&](uint32_t k) -> uint32_t {
+        if (k >= K) return 0u;
+        const unsigned long long t = tile0 + (unsigned long long)k * gridDim.x;
         const long long idx = (long long)(t * (unsigned long long)kTileBytes) - 1 - (long long)lane;
         return idx >= 0 ? (uint32_t)bytes[byte_of_symbol((unsigned long long)idx)] : 0u;
     };
+    const uint32_t wk = lane & (uint32_t)(kW - 1);          // the chunk this lane prepares (lanes 16..31 mirror)
+    const uint32_t ring_w = ring_window(wk);
 
-    uint32_t sym = 0;
-    for (uint32_t k = first;; k += 2u) {
+    uint32_t sym = tail_symbol(first);
+    for (uint32_t k = first; k < K; k += 2u) {
         const uint32_t slot = slot_of(k);
-        const unsigned long long tile = tile_of(p, k);
-        if (tile == kNoTile) break;
-        if (k == first) sym = tail_symbol(tile);
+        const unsigned long long tile = tile0 + (unsigned long long)k * gridDim.x;
         // this warp's next tile: its tail symbols have two tiles to land
-        const uint32_t sym_next = tail_symbol(tile_of(p, k + 2u));
+        const uint32_t sym_next = tail_symbol(k + 2u);
         long long t0 = prof.now();
-        mbar_wait(&ctrl->bar_agg[slot], par_of(k));
+        mbar_wait(kBarAggS + slot * 8u, par_of(k));
         prof.add(kProfWaitAgg, t0);
         prof.count(kProfTiles);
 
@@ -401,7 +418,6 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
             excl = p.start_bit + v;
         }
-        if (tile == p.end_tile - 1 && lane == 0) p.result->bits_end = excl + ctrl->btile[slot];
         prof.add(kProfLookback, t0);
 
         // ---------------- the (excl & 31) stream bits just before the tile ----------------
@@ -428,12 +444,52 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, Ctrl *ctrl, uint32_
             // fewer than `sh` bits in 32 symbols (zero-length codes): walk further back
             if (have < sh && first_sym > 32ULL) prev = bits_before<WIDE>(p, tab_s, first_sym, sh, lane);
         }
-        if (lane == 0) {
-            ctrl->prefix[slot] = excl;
-            ctrl->prev[slot] = prev;
-            ctrl->flags[slot] = (tile == p.n_tiles - 1) ? 1u : 0u;
-            mbar_arrive(&ctrl->bar_prefix[slot]);
+
+        // ---------------- the 16 copy-out records ----------------
+        const uint2 ch = lds_u64(kChunkS + (slot * kW + wk) * 8u);        // {ring position, bits}
+        const uint32_t n = ch.y;
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < kW; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d, kW);
+            if (wk >= (uint32_t)d) incl += v;
         }
+        const uint32_t btile = __shfl_sync(0xFFFFFFFFu, incl, kW - 1, kW);
+        if (tile == p.end_tile - 1 && lane == 0) p.result->bits_end = excl + btile;
+        const unsigned long long B = excl + (incl - n);                   // global bit offset of the chunk
+        const uint32_t shw = (uint32_t)B & 31u;
+        const unsigned long long g0 = B >> 5;
+        // the chunk's last (<= 31) bits, from its staged words (a chunk is contiguous in its ring)
+        uint32_t val = 0;
+        const uint32_t cnt = n < 31u ? n : 31u;
+        if (n) {
+            const uint32_t a = (n - 1u) >> 5, r = n & 31u;
+            const uint32_t addr = ring_w + ((ch.x & kRingMask) + a) * 4u;
+            const uint32_t w1 = lds_u32(addr);
+            const uint32_t w0 = a ? lds_u32(addr - 4u) : 0u;
+            val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
+        }
+        // the (< 32) bits that precede the chunk: its left neighbours' tails (one is enough unless a chunk is
+        // shorter than 31 bits), then the bits before the tile
+        uint32_t cin = 0, have = 0;
+        for (uint32_t d = 1; d < (uint32_t)kW; d++) {
+            const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, val, d, kW);
+            const uint32_t c = __shfl_up_sync(0xFFFFFFFFu, cnt, d, kW);
+            if (wk >= d && have < 31u) {
+                cin |= v << have;
+                have += c;
+            }
+            if (!__any_sync(0xFFFFFFFFu, wk > d && have < 31u)) break;
+        }
+        if (have < 31u) cin |= prev << have;
+        const uint32_t nfull = (shw + n) >> 5;                           // output words whose last bit is the chunk's
+        const bool last = tile == p.n_tiles - 1 && wk == (uint32_t)kW - 1;
+        const bool slow = last || g0 + nfull > p.out_cap_words;
+        if (lane < (uint32_t)kW)
+            sts_u128(kRecS + (slot * kW + wk) * 16u, (uint32_t)g0, (uint32_t)(g0 >> 32), cin,
+                     shw | (slow ? kRecSlow : 0u) | (last ? kRecLast : 0u));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(kBarPrefixS + slot * 8u);
         sym = sym_next;
         prof.add(kProfBitsBefore, t0);
     }
@@ -464,39 +520,30 @@ __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t
     }
 }
 
-// The chunk occupies the staged words at window address `st_s` onwards (contiguous: chunks never wrap).
-__device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, uint32_t st_s, uint32_t k, uint32_t n,
-                                         uint32_t warp, uint32_t lane)
+// The chunk (n bits) occupies the staged words at window address `st_s` onwards (contiguous: chunks never wrap);
+// `rec` is the resolver's record for it.
+__device__ __forceinline__ void copy_out(const EncParams &p, uint32_t st_s, uint32_t n, const uint4 rec,
+                                         uint32_t lane)
 {
-    const uint32_t slot = slot_of(k);
-    // the (< 32) bits that precede this chunk: neighbours' carries, then the tile's `prev`
-    uint32_t cin = 0, have = 0;
-    for (int r = (int)warp - 1; r >= 0 && have < 31u; r--) {
-        cin |= ctrl->carry_val[k & 15u][r] << have;
-        have += ctrl->carry_cnt[k & 15u][r];
-    }
-    if (have < 31u) cin |= ctrl->prev[slot] << have;
-
-    const unsigned long long B = ctrl->prefix[slot] + ctrl->woff[slot][warp];
-    const uint32_t sh = (uint32_t)(B & 31ULL);
-    const unsigned long long g0 = B >> 5;
-    const unsigned long long end = B + n;
-    const uint32_t nfull = (uint32_t)((end >> 5) - g0);        // words whose last bit is ours (<= ceil(n/32))
-    const bool last = ctrl->flags[slot] && warp == (uint32_t)kW - 1;   // the job's final word(s)
-    if (!last && g0 + nfull <= p.out_cap_words) {
+    const uint32_t sh = rec.w & 31u;
+    const uint32_t nfull = (sh + n) >> 5;                      // words whose last bit is ours (<= ceil(n/32))
+    const unsigned long long g0 = (unsigned long long)rec.y << 32 | rec.x;
+    if (!(rec.w & kRecSlow)) {
         // common case: every word this chunk owns comes from two neighbouring staged words
-        copy_run(p.out + g0, st_s, nfull, cin, sh, lane);
+        copy_run(p.out + g0, st_s, nfull, rec.z, sh, lane);
     } else {
+        // the job's final word(s), or an output buffer that is too small
+        const bool last = (rec.w & kRecLast) != 0;
         const uint32_t nwrite = nfull + (last ? 1u : 0u);
         const uint32_t nstage = (n + 31u) >> 5;
         bool spill = false;
         for (uint32_t j = lane; j < nwrite; j += 32u) {
             const uint32_t cur = (j < nstage) ? lds_u32(st_s + 4u * j) : 0u;
-            const uint32_t before = (j == 0) ? cin : ((j - 1 < nstage) ? lds_u32(st_s + 4u * j - 4u) : 0u);
+            const uint32_t before = (j == 0) ? rec.z : ((j - 1 < nstage) ? lds_u32(st_s + 4u * j - 4u) : 0u);
             const uint32_t v = __funnelshift_r(cur, before, sh);
             if (g0 + j < p.out_cap_words)
                 p.out[g0 + j] = v;
-            else if (!(last && j == nfull && (end & 31ULL) == 0))      // the courtesy zero word may not fit
+            else if (!(last && j == nfull && ((sh + n) & 31u) == 0))   // the courtesy zero word may not fit
                 spill = true;
         }
         if (spill) p.result->overflow = 1ULL;
@@ -505,8 +552,8 @@ __device__ __forceinline__ void copy_out(const EncParams &p, Ctrl *ctrl, uint32_
 
 // ---- worker warp ----------------------------------------------------------------------------------------
 template <int G, bool WIDE, bool CHECK>
-__device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl *ctrl, uint32_t warp,
-                       uint32_t lane)
+__device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint32_t warp, uint32_t lane,
+                       uint32_t K)
 {
     constexpr int NG = (S + G - 1) / G;
     // byte 0 = lane*4, bytes 1..2 = bytes 2..3 of the table's window address (prmt source b)
@@ -524,44 +571,47 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
 
+    // this warp's chunk of tile t is chunk t * kW + warp of the input, kChunkWords words.  It is `full` when it
+    // lies entirely inside the input: tiles only grow with k, so that holds for the iterations [0, KF)
+    const unsigned long long tile0 = p.first_tile + blockIdx.x;
+    const unsigned long long full_chunks = p.n_words / (unsigned long long)kChunkWords;
+    unsigned long long tf = full_chunks > warp ? (full_chunks - warp + (unsigned long long)(kW - 1)) / kW : 0ULL;
+    if (tf > p.end_tile) tf = p.end_tile;
+    const uint32_t KF = tf > tile0 ? (uint32_t)((tf - tile0 + gridDim.x - 1) / gridDim.x) : 0u;
+    const unsigned long long step = (unsigned long long)gridDim.x * kTileWords;
+    // the lane's words of the current chunk
+    const uint32_t *src = p.in + (tile0 * kW + warp) * (unsigned long long)kChunkWords + lane * (uint32_t)kLaneWords;
+    const uint32_t my_chunk_s = kChunkS + warp * 8u;           // chunk[slot][warp] = my_chunk_s + slot * kW * 8
+    const uint32_t my_rec_s = kRecS + warp * 16u;
+
     // ---- the staging ring: the chunks [retired, emitted) of this worker occupy ring positions [tail, head);
     //      positions are absolute word counters, the index is position mod size; a chunk never wraps (the
     //      words up to the end of the ring are skipped instead)
     uint32_t emitted = 0, retired = 0, head = 0, tail = 0;
-    auto retire = [&](bool blocking) {
-        const uint32_t k = retired, slot = slot_of(k);
-        {
-            // the offset needs every worker's count, the carries every worker's bits: both are posted together
-            const long long t0 = prof.now();
-            if (blocking) mbar_wait(&ctrl->bar_prefix[slot], par_of(k));
-            prof.add(kProfWaitPrefix, t0);
-        }
+    // copy out the oldest staged chunk (its record has been posted)
+    auto retire = [&]() {
         const long long t0 = prof.now();
-        const uint2 ch = ctrl->chunk[warp][slot];
-        copy_out(p, ctrl, ring_s + (ch.x & kRingMask) * 4u, k, ch.y, warp, lane);
+        const uint32_t slot = slot_of(retired);
+        const uint4 rec = lds_u128(my_rec_s + slot * (kW * 16u));
+        const uint2 ch = lds_u64(my_chunk_s + slot * (kW * 8u));
+        copy_out(p, ring_s + (ch.x & kRingMask) * 4u, ch.y, rec, lane);
         retired++;
-        tail = (retired < emitted) ? ctrl->chunk[warp][slot_of(retired)].x : head;
-        __syncwarp();
+        tail = (retired < emitted) ? lds_u32(my_chunk_s + slot_of(retired) * (kW * 8u)) : head;
+        __syncwarp();                                          // the staged words may be overwritten from here on
         prof.add(kProfCopy, t0);
     };
-
-    // this warp's chunk of tile t is chunk t * kW + warp of the input, kChunkWords words; it is `full` when it
-    // lies entirely inside the input
-    const unsigned long long full_chunks = p.n_words / (unsigned long long)kChunkWords;
-    const uint32_t *in_lane = p.in + lane * (uint32_t)kLaneWords;
-    auto chunk_index = [&](unsigned long long t) { return t * (unsigned long long)kW + warp; };
+    auto wait_record = [&]() {
+        const long long t0 = prof.now();
+        mbar_wait(kBarPrefixS + slot_of(retired) * 8u, par_of(retired));
+        prof.add(kProfWaitPrefix, t0);
+    };
 
     uint32_t w[kLaneWords];
-    unsigned long long tile = tile_of(p, 0);
-    bool full = tile != kNoTile && chunk_index(tile) < full_chunks;
-    if (full) ld_lane(in_lane + chunk_index(tile) * (unsigned long long)kChunkWords, w);
+    if (KF) ld_lane(src, w);
 
-    for (; tile != kNoTile;) {
-        const uint32_t k = emitted, slot = slot_of(k);
-        // slot k % kDepth still belongs to tile k - kDepth until that one has been copied out
-        if (emitted - retired >= (uint32_t)kDepth) retire(true);
-        const unsigned long long tnext = tile_of(p, k + 1u);
-        const bool full_next = tnext != kNoTile && chunk_index(tnext) < full_chunks;
+    for (uint32_t k = 0; k < K; k++) {
+        const uint32_t slot = slot_of(k);
+        const bool full = k < KF, full_next = k + 1u < KF;
         long long t0 = prof.now();
 
         // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
@@ -592,7 +642,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                 }
             }
         } else {
-            const unsigned long long sym0 = chunk_index(tile) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
+            const unsigned long long tile = tile0 + (unsigned long long)k * gridDim.x;
+            const unsigned long long sym0 =
+                (tile * kW + warp) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
 #pragma unroll 1
             for (int i = 0; i < S; i++) {
                 if (sym0 + i < n_bytes) {
@@ -606,12 +658,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         }
         // Pass 1 has consumed `w`: request the next chunk now; it has the rest of this tile to arrive.  (One set
         // of input registers instead of two: measured +5-7 %, and no scoreboard aliasing between the two loads.)
-        if (full_next) ld_lane(in_lane + chunk_index(tnext) * (unsigned long long)kChunkWords, w);
-        if (p.l2_prefetch) {
-            const unsigned long long t2 = tile_of(p, k + 2u);
-            if (t2 != kNoTile && chunk_index(t2) < full_chunks)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(in_lane + chunk_index(t2) * (unsigned long long)kChunkWords));
-        }
+        if (full_next) ld_lane(src + step, w);
+        if (p.l2_prefetch && k + 2u < KF) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2u * step));
         prof.add(kProfPass1, t0);
         t0 = prof.now();
 
@@ -626,7 +674,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         const uint32_t need = n ? ((n + 31u) >> 5) : 1u;
         if ((head & kRingMask) + need > kRingWords) head = (head | kRingMask) + 1u;   // skip to the ring start
         if (emitted == retired) tail = head;                   // nothing staged: the ring is empty wherever we are
-        while (head + need - tail > kRingWords) retire(true);
+        while (head + need - tail > kRingWords) {
+            wait_record();
+            retire();
+        }
         const uint32_t st_s = ring_s + (head & kRingMask) * 4u;    // window address of the chunk's first word
 
         // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
@@ -634,6 +685,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
         if (fast) {
             const uint32_t wa0 = st_s + (q0 >> 5) * 4u;       // the word this lane starts in
+            uint32_t wa = wa0;                                // the word being filled
             uint32_t q = q0;                                  // chunk-relative bit position (the only serial chain)
             uint32_t lo_prev = 0;
             if (CHECK && (ormask & ~31u)) {
@@ -641,7 +693,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                 // symbol at a time -- a single codeword (< 32 bits) always fits.  `w` already belongs to the next
                 // chunk, so the lane's symbols are read again.
                 uint32_t wf[kLaneWords];
-                ld_lane(in_lane + chunk_index(tile) * (unsigned long long)kChunkWords, wf);
+                ld_lane(src, wf);
 #pragma unroll
                 for (int i = 0; i < S; i++) {
                     const uint32_t off = __byte_perm(wf[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
@@ -649,26 +701,26 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
                     const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
                     const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
                     const uint32_t qn = q + l;
-                    if ((qn ^ q) >= 32u)
-                        sts_u32(st_s + (q >> 5) * 4u, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+                    if ((qn ^ q) & 32u) {
+                        sts_u32(wa, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+                        wa += 4u;
+                    }
                     q = qn;
                     lo_prev = lo_new;
                 }
             } else {
-                uint32_t r = q0 & 31u;                        // bits already in the word being filled
-                uint32_t wa = wa0;                            // that word's address
 #pragma unroll
                 for (int g = 0; g < NG; g++) {
-                    r += gss[g];
-                    if (r >= 32u) {
-                        // the 32 bits that end at the boundary: the low (r & 31) of them come from the window
-                        // before this group, the rest from the window after it (funnel shifts use r mod 32)
+                    // a group is < 32 bits: it completes at most one word, and does so iff bit 5 of q flips
+                    const uint32_t qn = q + gss[g];
+                    if ((qn ^ q) & 32u) {
+                        // the 32 bits that end at the boundary: the low (qn & 31) of them come from the window
+                        // before this group, the rest from the window after it (funnel shifts use qn mod 32)
                         const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                        sts_u32(wa, __funnelshift_r(los[g], hi, r));
+                        sts_u32(wa, __funnelshift_r(los[g], hi, qn));
                         wa += 4u;
-                        r -= 32u;
                     }
-                    q += gss[g];
+                    q = qn;
                     lo_prev = los[g];
                 }
             }
@@ -676,9 +728,11 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
             const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
             const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
             if (lane != 0 && (q0 & 31u)) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
-            if (lane == 31 && r) sts_u32(st_s + (q >> 5) * 4u, tailw);             // the word that holds bit n
+            if (lane == 31 && r) sts_u32(wa, tailw);                               // the word that holds bit n
         } else {
-            const unsigned long long sym0 = chunk_index(tile) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
+            const unsigned long long tile = tile0 + (unsigned long long)k * gridDim.x;
+            const unsigned long long sym0 =
+                (tile * kW + warp) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
             for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) sts_u32(st_s + 4u * j, 0u);
             __syncwarp();
             uint32_t *st = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(st_s));
@@ -704,34 +758,28 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, Ctrl
         __syncwarp();
         prof.add(kProfEmit, t0);
 
-        // ---------------- the chunk is staged: count, carry, hand-offs ----------------
+        // ---------------- the chunk is staged: post {ring position, bits} ----------------
         if (lane == 0) {
-            // carry: the last (<= 31) bits of this chunk, for the right-hand neighbour
-            uint32_t val = 0;
-            if (n) {
-                const uint32_t a = (n - 1u) >> 5, r = n & 31u;
-                const uint32_t w1 = lds_u32(st_s + 4u * a);
-                const uint32_t w0 = a ? lds_u32(st_s + 4u * a - 4u) : 0u;
-                val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
-            }
-            ctrl->carry_val[k & 15u][warp] = val;
-            ctrl->carry_cnt[k & 15u][warp] = n < 31u ? n : 31u;
-            ctrl->chunk[warp][slot] = make_uint2(head, n);
-            ctrl->sums[slot][warp] = n;
-            mbar_arrive(&ctrl->bar_sums[slot]);
+            sts_u64(my_chunk_s + slot * (kW * 8u), head, n);
+            mbar_arrive(kBarSumsS + slot * 8u);
         }
         head += need;
         emitted++;
-        __syncwarp();
 
-        // ---------------- copy out every chunk whose global offset is already known ----------------
-        while (retired < emitted && mbar_test(&ctrl->bar_prefix[slot_of(retired)], par_of(retired)))
-            retire(false);
-
-        tile = tnext;
-        full = full_next;
+        // ---------------- copy out every chunk whose record is already there; never hold kDepth of them ----------------
+        while (retired < emitted) {
+            if (!mbar_test(kBarPrefixS + slot_of(retired) * 8u, par_of(retired))) {
+                if (emitted - retired < (uint32_t)kDepth) break;
+                wait_record();
+            }
+            retire();
+        }
+        src += step;
     }
-    while (retired < emitted) retire(true);
+    while (retired < emitted) {
+        wait_record();
+        retire();
+    }
     prof.add(kProfWorker, t_worker);
     prof.flush(p, lane);
 }
@@ -743,13 +791,12 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     extern __shared__ __align__(1024) uint32_t smem[];
     unsigned char *base = reinterpret_cast<unsigned char *>(smem);
     uint32_t *tab = reinterpret_cast<uint32_t *>(base + kTabOffset);
-    Ctrl *ctrl = reinterpret_cast<Ctrl *>(base + kCtrlOffset);
-    const uint32_t tab_s = smem_addr(tab);
-    if (tab_s != kTabWindow) {
+    if (smem_addr(tab) != kTabWindow) {
         // the shared window is not laid out as assumed: refuse loudly instead of mis-encoding
         if (threadIdx.x == 0) p.result->overflow = 2ULL;
         return;
     }
+    constexpr uint32_t tab_s = kTabWindow;                  // window addresses are compile-time constants from here on
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
@@ -761,24 +808,24 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
         p.tree_zero[i] = 0ULL;
     fill_table<WIDE>(tab, p.table, tid);
     if (tid == 0) {
-        for (int i = 0; i < kDepth; i++) {
-            mbar_init(&ctrl->bar_sums[i], kW);
-            mbar_init(&ctrl->bar_agg[i], 1);
-            mbar_init(&ctrl->bar_prefix[i], 1);
+        for (uint32_t i = 0; i < (uint32_t)kDepth; i++) {
+            mbar_init(kBarSumsS + i * 8u, kW);
+            mbar_init(kBarAggS + i * 8u, 1);
+            mbar_init(kBarPrefixS + i * 8u, 1);
         }
     }
     __syncthreads();
 
-    if (warp < (uint32_t)kW) {
-        uint32_t *ring = reinterpret_cast<uint32_t *>(
-            warp < (uint32_t)kRingsBelow ? base + kRingsBelowOffset + warp * kRingBytes
-                                         : base + kRingsAboveOffset + (warp - kRingsBelow) * kRingBytes);
-        worker<G, WIDE, CHECK>(p, tab_s, smem_addr(ring), ctrl, warp, lane);
-    } else if (warp == (uint32_t)kPublisherWarp) {
-        publisher(p, ctrl, lane);
-    } else {
-        resolver<WIDE>(p, tab_s, ctrl, lane, warp - (uint32_t)kResolverWarp);
-    }
+    // CTA b takes tiles first_tile + b, + grid, + 2 grid, ...: K of them (the grid never exceeds the tile count)
+    const unsigned long long span = p.end_tile - p.first_tile;
+    const uint32_t K = blockIdx.x < span ? (uint32_t)((span - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+
+    if (warp < (uint32_t)kW)
+        worker<G, WIDE, CHECK>(p, tab_s, ring_window(warp), warp, lane, K);
+    else if (warp == (uint32_t)kPublisherWarp)
+        publisher(p, lane, K);
+    else
+        resolver<WIDE>(p, tab_s, lane, warp - (uint32_t)kResolverWarp, K);
 }
 
 template <bool WIDE>
@@ -912,3 +959,4 @@ cudaError_t launch_encode(const EncVariant &v, const EncParams &p, int grid, cud
 }
 
 }  // namespace hb
+
