@@ -228,6 +228,17 @@ __device__ __forceinline__ void sts_u128(uint32_t addr, uint32_t x, uint32_t y, 
 {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+// one step of an inclusive warp scan: the shuffle's own predicate says whether a source lane exists
+__device__ __forceinline__ uint32_t scan_step(uint32_t v, uint32_t d)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 t;\n\t"
+        "shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t"
+        "@p add.u32 %0, %0, t;\n\t}"
+        : "+r"(v)
+        : "r"(d));
+    return v;
+}
 // ---- optional cycle accounting: build with -DHB_PROFILE and run with $HB_PROFILE=1 --------------------
 enum { kProfWaitTile = 0, kProfWaitPrefix, kProfWorker, kProfWaitSums, kProfWaitAgg, kProfLookback,
        kProfBitsBefore, kProfResolver, kProfTiles, kProfPolls, kProfPass1, kProfEmit, kProfCopy, kProfCount };
@@ -506,6 +517,7 @@ __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t
     // two words per lane per trip, every trip independent of the others (loads first, then stores)
     uint32_t a = src_s + lane * 4u;
     uint32_t *o = out + lane;
+#pragma unroll 1
     for (uint32_t j = lane; j < cnt; j += 64u, a += 256u, o += 64) {
         const bool two = j + 32u < cnt;
         const uint32_t c0 = lds_free(a);
@@ -560,13 +572,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
     const uint32_t laneoff = lane * 4u | ((tab_s >> 16) << 8);
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     const unsigned long long n_bytes = p.n_words * 4ULL;
-    // the warp scan adds a neighbour's value when lane >= distance: as multiplicands for one IMAD per step
-    uint32_t scan_on[5];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        scan_on[i] = lane >= (1u << i) ? 1u : 0u;
-        asm volatile("" : "+r"(scan_on[i]));                  // keep it a multiplicand (IMAD), not a compare + select
-    }
 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
@@ -666,7 +671,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         // ---------------- warp scan: this lane's bit offset inside the chunk ----------------
         uint32_t incl = bt;
 #pragma unroll
-        for (int i = 0; i < 5; i++) incl += __shfl_up_sync(0xFFFFFFFFu, incl, 1u << i) * scan_on[i];
+        for (int i = 0; i < 5; i++) incl = scan_step(incl, 1u << i);
         const uint32_t q0 = incl - bt;
         const uint32_t n = __shfl_sync(0xFFFFFFFFu, incl, 31);
 
@@ -766,14 +771,14 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         head += need;
         emitted++;
 
-        // ---------------- copy out every chunk whose record is already there; never hold kDepth of them ----------------
-        while (retired < emitted) {
-            if (!mbar_test(kBarPrefixS + slot_of(retired) * 8u, par_of(retired))) {
-                if (emitted - retired < (uint32_t)kDepth) break;
-                wait_record();
-            }
-            retire();
+        // ---------------- copy out the oldest staged chunk if its record is there; never hold kDepth of them -----------
+        // (one per iteration matches the rate of emission: the backlog settles where records are always ready)
+        bool ready = mbar_test(kBarPrefixS + slot_of(retired) * 8u, par_of(retired));
+        if (!ready && emitted - retired >= (uint32_t)kDepth) {
+            wait_record();
+            ready = true;
         }
+        if (ready) retire();
         src += step;
     }
     while (retired < emitted) {
