@@ -293,18 +293,36 @@ __device__ __forceinline__ void fetch_entry(uint32_t tab_s, uint32_t sym, uint32
     c = tab_ld(addr);
     len = WIDE ? tab_ld_len(addr) : (c & 0xFFu);
 }
+// One global round trip: every warp fetches its symbols' entries first (a broadcast load each), then writes them,
+// one conflict-free row of 32 lanes per symbol.  (The second half of a packed slot is never read.)
 template <bool WIDE>
-__device__ __forceinline__ void fill_table(uint32_t *tab, const uint32_t *g, uint32_t tid)
+__device__ __forceinline__ void fill_table(uint32_t tab_s, const uint32_t *g, uint32_t warp, uint32_t lane)
 {
     // packed source: uint32[256]; wide source: {cw_left, len}[256]
-    for (uint32_t i = tid; i < 256u * 64u; i += kEncThreads) {
-        const uint32_t sym = i >> 6, k = i & 63u;
-        uint32_t v = 0;
-        if (WIDE)
-            v = __ldg(g + 2u * sym + (k >> 5));
-        else if (k < 32u)
-            v = __ldg(g + sym);
-        tab[i] = v;
+    constexpr int kWarps = kEncThreads / 32;
+    constexpr int kIter = (256 + kWarps - 1) / kWarps;
+    uint32_t e[kIter], l[kIter];
+#pragma unroll
+    for (int i = 0; i < kIter; i++) {
+        const uint32_t sym = warp + (uint32_t)(i * kWarps);
+        e[i] = l[i] = 0;
+        if (sym < 256u) {
+            if (WIDE) {
+                e[i] = __ldg(g + 2u * sym);
+                l[i] = __ldg(g + 2u * sym + 1u);
+            } else {
+                e[i] = __ldg(g + sym);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kIter; i++) {
+        const uint32_t sym = warp + (uint32_t)(i * kWarps);
+        if (sym < 256u) {
+            const uint32_t addr = tab_s + sym * kSlotStride + lane * 4u;
+            sts_u32(addr, e[i]);
+            if (WIDE) sts_u32(addr + 128u, l[i]);
+        }
     }
 }
 
@@ -575,6 +593,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
+#ifdef HB_WA_IMAD
+    uint32_t one = 1u;
+    asm volatile("" : "+r"(one));
+#endif
 
     // this warp's chunk of tile t is chunk t * kW + warp of the input, kChunkWords words.  It is `full` when it
     // lies entirely inside the input: tiles only grow with k, so that holds for the iterations [0, KF)
@@ -723,7 +745,11 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         // before this group, the rest from the window after it (funnel shifts use qn mod 32)
                         const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
                         sts_u32(wa, __funnelshift_r(los[g], hi, qn));
+#ifdef HB_WA_IMAD
+                        asm("mad.lo.u32 %0, %1, 4, %0;" : "+r"(wa) : "r"(one));     // fma pipe: the alu pipe is the busy one
+#else
                         wa += 4u;
+#endif
                     }
                     q = qn;
                     lo_prev = los[g];
@@ -811,7 +837,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     for (unsigned long long i = (unsigned long long)blockIdx.x * kEncThreads + tid; i < p.zero_count;
          i += (unsigned long long)gridDim.x * kEncThreads)
         p.tree_zero[i] = 0ULL;
-    fill_table<WIDE>(tab, p.table, tid);
+    fill_table<WIDE>(tab_s, p.table, warp, lane);
     if (tid == 0) {
         for (uint32_t i = 0; i < (uint32_t)kDepth; i++) {
             mbar_init(kBarSumsS + i * 8u, kW);
