@@ -82,14 +82,14 @@ constexpr uint32_t kTabWindow = 0x10000;
 constexpr uint32_t kTabOffset = kTabWindow - kSmemReserved;          // offsets are inside the dynamic block
 constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
 constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
-constexpr uint32_t kRingBytes = kRingWords * 4;
+constexpr uint32_t kRingBytes = (kRingWords + kRingWords / 32) * 4;     // physical: room for one pad word per 32 (ring_at)
 constexpr uint32_t kRingMask = kRingWords - 1;
-constexpr int kRingsBelow = 7;                          // rings that fit under the table
+constexpr int kRingsBelow = 6;                          // rings that fit under the table
 constexpr uint32_t kRingsBelowOffset = 0x2000 - kSmemReserved;
 constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
 constexpr uint32_t kCtrlOffset = 0;
 constexpr uint32_t kSmemBytes = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
-static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes == kTabOffset, "rings 0..6 end where the table starts");
+static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes <= kTabOffset, "rings 0..5 end before the table starts");
 // a chunk is staged contiguously (it never wraps) and must fit even when every symbol takes the longest code
 static_assert((uint32_t)S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
 
@@ -122,6 +122,25 @@ __device__ __forceinline__ uint32_t ring_window(uint32_t w)
     return w < (uint32_t)kRingsBelow ? kSmemReserved + kRingsBelowOffset + w * kRingBytes
                                      : kSmemReserved + kRingsAboveOffset + (w - (uint32_t)kRingsBelow) * kRingBytes;
 }
+
+// Kernels for long codes (small G) stage with the padded ring layout.
+__host__ __device__ constexpr bool swizzled(int group) { return group <= 3; }
+// Window address of logical word `idx` (< kRingWords) of a ring.  SWZ: one pad word after every 32.  A lane's write
+// position in pass 2 is about (bits per symbol) * 2 words per lane: at 4 or 8 bits per symbol the lanes are 8 or 16
+// words apart and a plain layout puts the stores of a warp into 4 or 2 banks; with the pad they fall into 32.
+template <bool SWZ>
+__device__ __forceinline__ uint32_t ring_at(uint32_t ring_s, uint32_t idx)
+{
+    return ring_s + (SWZ ? __umulhi(idx, 1u << 27) + idx : idx) * 4u;     // idx + (idx >> 5), on the fma pipe
+}
+// A position in a ring that advances word by word (pass 2 stores).
+template <bool SWZ>
+struct RingCursor {
+    uint32_t v;                                             // SWZ: logical word index, else: window address
+    __device__ __forceinline__ RingCursor(uint32_t ring_s, uint32_t idx) : v(SWZ ? idx : ring_s + idx * 4u) {}
+    __device__ __forceinline__ uint32_t addr(uint32_t ring_s) const { return SWZ ? ring_at<true>(ring_s, v) : v; }
+    __device__ __forceinline__ void next() { v += SWZ ? 1u : 4u; }
+};
 
 // ---- small PTX helpers --------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p)
@@ -219,6 +238,10 @@ __device__ __forceinline__ uint32_t lds_free(uint32_t addr)
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
 {
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y)
 {
@@ -395,7 +418,7 @@ __device__ void publisher(const EncParams &p, uint32_t lane, uint32_t K)
 // bit offset (look-back result + scan of the 16 counts), hence its first output word and phase, and the (< 32)
 // stream bits that precede it, taken from the left neighbours' staged words (or, for chunk 0, re-derived from
 // the 32 symbols before the tile: no inter-CTA data dependency).
-template <bool WIDE>
+template <bool WIDE, bool SWZ>
 __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint32_t first, uint32_t K)
 {
     Prof prof(p, first == 0);
@@ -493,9 +516,9 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
         const uint32_t cnt = n < 31u ? n : 31u;
         if (n) {
             const uint32_t a = (n - 1u) >> 5, r = n & 31u;
-            const uint32_t addr = ring_w + ((ch.x & kRingMask) + a) * 4u;
-            const uint32_t w1 = lds_u32(addr);
-            const uint32_t w0 = a ? lds_u32(addr - 4u) : 0u;
+            const uint32_t i1 = (ch.x & kRingMask) + a;
+            const uint32_t w1 = lds_u32(ring_at<SWZ>(ring_w, i1));
+            const uint32_t w0 = a ? lds_u32(ring_at<SWZ>(ring_w, i1 - 1u)) : 0u;
             val = (r ? __funnelshift_l(w1, w0, r) : w1) & 0x7FFFFFFFu;
         }
         // the (< 32) bits that precede the chunk: its left neighbours' tails (one is enough unless a chunk is
@@ -527,40 +550,46 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
 }
 
 // ---- worker: copy one staged chunk to its place in the global stream ---------------------------------
-// `cnt` output words from a run of staged words: out[j] = the 32 bits that start `sh` bits before staged word j;
-// word 0 takes those leading bits from `first_before`.
-__device__ __forceinline__ void copy_run(uint32_t *out, uint32_t src_s, uint32_t cnt, uint32_t first_before,
-                                         uint32_t sh, uint32_t lane)
+// `cnt` output words from the staged words i0, i0 + 1, ... of the ring: out[j] = the 32 bits that start `sh` bits
+// before staged word j; word 0 takes those leading bits from `first_before`.
+template <bool SWZ>
+__device__ __forceinline__ void copy_run(uint32_t *out, uint32_t ring_s, uint32_t i0, uint32_t cnt,
+                                         uint32_t first_before, uint32_t sh, uint32_t lane)
 {
-    // two words per lane per trip, every trip independent of the others (loads first, then stores)
-    uint32_t a = src_s + lane * 4u;
+    // two words per lane per trip, every trip independent of the others (loads first, then stores).  A row of 32
+    // staged words further on is 32 (+ 1 pad) words further on in the ring, whatever the alignment of i0.
+    constexpr uint32_t kRow = SWZ ? 132u : 128u;
+    const uint32_t idx = i0 + lane;
+    uint32_t a = ring_at<SWZ>(ring_s, idx);                   // this lane's word of the row
+    uint32_t b = a - ((SWZ && (idx & 31u) == 0) ? 8u : 4u);   // and its predecessor (not used for word 0): a pad between
     uint32_t *o = out + lane;
 #pragma unroll 1
-    for (uint32_t j = lane; j < cnt; j += 64u, a += 256u, o += 64) {
+    for (uint32_t j = lane; j < cnt; j += 64u, a += 2u * kRow, b += 2u * kRow, o += 64) {
         const bool two = j + 32u < cnt;
         const uint32_t c0 = lds_free(a);
-        const uint32_t b0 = j ? lds_free(a - 4u) : first_before;       // only word 0 lacks a staged predecessor
+        const uint32_t b0 = j ? lds_free(b) : first_before;           // only word 0 lacks a staged predecessor
         uint32_t c1 = 0, b1 = 0;
         if (two) {
-            c1 = lds_free(a + 128u);
-            b1 = lds_free(a + 124u);
+            c1 = lds_free(a + kRow);
+            b1 = lds_free(b + kRow);
         }
         o[0] = __funnelshift_r(c0, b0, sh);
         if (two) o[32] = __funnelshift_r(c1, b1, sh);
     }
 }
 
-// The chunk (n bits) occupies the staged words at window address `st_s` onwards (contiguous: chunks never wrap);
+// The chunk (n bits) occupies the staged words i0 onwards of the ring (contiguous: chunks never wrap);
 // `rec` is the resolver's record for it.
-__device__ __forceinline__ void copy_out(const EncParams &p, uint32_t st_s, uint32_t n, const uint4 rec,
-                                         uint32_t lane)
+template <bool SWZ>
+__device__ __forceinline__ void copy_out(const EncParams &p, uint32_t ring_s, uint32_t i0, uint32_t n,
+                                         const uint4 rec, uint32_t lane)
 {
     const uint32_t sh = rec.w & 31u;
     const uint32_t nfull = (sh + n) >> 5;                      // words whose last bit is ours (<= ceil(n/32))
     const unsigned long long g0 = (unsigned long long)rec.y << 32 | rec.x;
     if (!(rec.w & kRecSlow)) {
         // common case: every word this chunk owns comes from two neighbouring staged words
-        copy_run(p.out + g0, st_s, nfull, rec.z, sh, lane);
+        copy_run<SWZ>(p.out + g0, ring_s, i0, nfull, rec.z, sh, lane);
     } else {
         // the job's final word(s), or an output buffer that is too small
         const bool last = (rec.w & kRecLast) != 0;
@@ -568,8 +597,9 @@ __device__ __forceinline__ void copy_out(const EncParams &p, uint32_t st_s, uint
         const uint32_t nstage = (n + 31u) >> 5;
         bool spill = false;
         for (uint32_t j = lane; j < nwrite; j += 32u) {
-            const uint32_t cur = (j < nstage) ? lds_u32(st_s + 4u * j) : 0u;
-            const uint32_t before = (j == 0) ? rec.z : ((j - 1 < nstage) ? lds_u32(st_s + 4u * j - 4u) : 0u);
+            const uint32_t cur = (j < nstage) ? lds_u32(ring_at<SWZ>(ring_s, i0 + j)) : 0u;
+            const uint32_t before =
+                (j == 0) ? rec.z : ((j - 1 < nstage) ? lds_u32(ring_at<SWZ>(ring_s, i0 + j - 1u)) : 0u);
             const uint32_t v = __funnelshift_r(cur, before, sh);
             if (g0 + j < p.out_cap_words)
                 p.out[g0 + j] = v;
@@ -586,6 +616,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                        uint32_t K)
 {
     constexpr int NG = (S + G - 1) / G;
+    constexpr bool SWZ = swizzled(G);
     // byte 0 = lane*4, bytes 1..2 = bytes 2..3 of the table's window address (prmt source b)
     const uint32_t laneoff = lane * 4u | ((tab_s >> 16) << 8);
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
@@ -593,10 +624,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
 
     Prof prof(p, warp == 0);
     const long long t_worker = prof.now();
-#ifdef HB_WA_IMAD
-    uint32_t one = 1u;
-    asm volatile("" : "+r"(one));
-#endif
 
     // this warp's chunk of tile t is chunk t * kW + warp of the input, kChunkWords words.  It is `full` when it
     // lies entirely inside the input: tiles only grow with k, so that holds for the iterations [0, KF)
@@ -621,7 +648,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         const uint32_t slot = slot_of(retired);
         const uint4 rec = lds_u128(my_rec_s + slot * (kW * 16u));
         const uint2 ch = lds_u64(my_chunk_s + slot * (kW * 8u));
-        copy_out(p, ring_s + (ch.x & kRingMask) * 4u, ch.y, rec, lane);
+        copy_out<SWZ>(p, ring_s, ch.x & kRingMask, ch.y, rec, lane);
         retired++;
         tail = (retired < emitted) ? lds_u32(my_chunk_s + slot_of(retired) * (kW * 8u)) : head;
         __syncwarp();                                          // the staged words may be overwritten from here on
@@ -705,14 +732,14 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
             wait_record();
             retire();
         }
-        const uint32_t st_s = ring_s + (head & kRingMask) * 4u;    // window address of the chunk's first word
+        const uint32_t i0 = head & kRingMask;                  // the chunk's first word in the ring
 
         // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
         // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
         const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
         if (fast) {
-            const uint32_t wa0 = st_s + (q0 >> 5) * 4u;       // the word this lane starts in
-            uint32_t wa = wa0;                                // the word being filled
+            const uint32_t wa0 = ring_at<SWZ>(ring_s, i0 + (q0 >> 5));   // the word this lane starts in
+            RingCursor<SWZ> wa(ring_s, i0 + (q0 >> 5));                  // the word being filled
             uint32_t q = q0;                                  // chunk-relative bit position (the only serial chain)
             uint32_t lo_prev = 0;
             if (CHECK && (ormask & ~31u)) {
@@ -729,8 +756,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                     const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
                     const uint32_t qn = q + l;
                     if ((qn ^ q) & 32u) {
-                        sts_u32(wa, __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
-                        wa += 4u;
+                        sts_u32(wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+                        wa.next();
                     }
                     q = qn;
                     lo_prev = lo_new;
@@ -744,12 +771,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         // the 32 bits that end at the boundary: the low (qn & 31) of them come from the window
                         // before this group, the rest from the window after it (funnel shifts use qn mod 32)
                         const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                        sts_u32(wa, __funnelshift_r(los[g], hi, qn));
-#ifdef HB_WA_IMAD
-                        asm("mad.lo.u32 %0, %1, 4, %0;" : "+r"(wa) : "r"(one));     // fma pipe: the alu pipe is the busy one
-#else
-                        wa += 4u;
-#endif
+                        sts_u32(wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
+                        wa.next();
                     }
                     q = qn;
                     lo_prev = los[g];
@@ -759,14 +782,13 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
             const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
             const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
             if (lane != 0 && (q0 & 31u)) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
-            if (lane == 31 && r) sts_u32(wa, tailw);                               // the word that holds bit n
+            if (lane == 31 && r) sts_u32(wa.addr(ring_s), tailw);                  // the word that holds bit n
         } else {
             const unsigned long long tile = tile0 + (unsigned long long)k * gridDim.x;
             const unsigned long long sym0 =
                 (tile * kW + warp) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
-            for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) sts_u32(st_s + 4u * j, 0u);
+            for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) sts_u32(ring_at<SWZ>(ring_s, i0 + j), 0u);
             __syncwarp();
-            uint32_t *st = reinterpret_cast<uint32_t *>(__cvta_shared_to_generic(st_s));
             uint32_t q = q0, lo = 0;
 #pragma unroll 1
             for (int i = 0; i < S; i++) {
@@ -777,14 +799,15 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         const uint32_t ln = __funnelshift_l(cwl, lo, l);
                         const uint32_t qn = q + l;
                         if ((qn ^ q) & ~31u)
-                            atomicOr(&st[(qn >> 5) - 1u], __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
+                            red_or_shared(ring_at<SWZ>(ring_s, i0 + (qn >> 5) - 1u),
+                                          __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
                         q = qn;
                         lo = ln;
                     }
                 }
             }
             const uint32_t f = q & 31u;
-            if (f) atomicOr(&st[q >> 5], lo << (32u - f));
+            if (f) red_or_shared(ring_at<SWZ>(ring_s, i0 + (q >> 5)), lo << (32u - f));
         }
         __syncwarp();
         prof.add(kProfEmit, t0);
@@ -856,7 +879,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     else if (warp == (uint32_t)kPublisherWarp)
         publisher(p, lane, K);
     else
-        resolver<WIDE>(p, tab_s, lane, warp - (uint32_t)kResolverWarp, K);
+        resolver<WIDE, swizzled(G)>(p, tab_s, lane, warp - (uint32_t)kResolverWarp, K);
 }
 
 template <bool WIDE>
