@@ -52,6 +52,13 @@
  */
 #include "hb_kernels.cuh"
 
+#ifndef HB_WAIT_NS
+#define HB_WAIT_NS 200
+#endif
+#ifndef HB_POLL_NS
+#define HB_POLL_NS 400
+#endif
+
 namespace hb {
 namespace {
 
@@ -80,7 +87,10 @@ constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
 constexpr uint32_t kTabWindow = 0x10000;
 constexpr uint32_t kTabOffset = kTabWindow - kSmemReserved;          // offsets are inside the dynamic block
-constexpr int kDepth = 8;                               // tiles a CTA may hold between encode and copy-out
+#ifndef HB_DEPTH
+#define HB_DEPTH 16
+#endif
+constexpr int kDepth = HB_DEPTH;                               // tiles a CTA may hold between encode and copy-out
 constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
 constexpr uint32_t kRingBytes = (kRingWords + kRingWords / 32) * 4;     // physical: room for one pad word per 32 (ring_at)
 constexpr uint32_t kRingMask = kRingWords - 1;
@@ -97,7 +107,8 @@ static_assert((uint32_t)S * 31u + 2u <= kRingWords, "a ring must hold one worst-
 // Control block at the start of the dynamic block.  Everything in it is addressed through the shared WINDOW
 // (plain ld/st.shared on 32-bit addresses): generic pointers cost a conversion on every access.
 struct Ctrl {
-    unsigned long long bar_sums[kDepth];        // workers -> publisher: the 16 chunks of tile k are staged
+    unsigned long long bar_sums[kDepth];        // workers -> publisher: the 16 chunk bit counts of tile k are posted
+    unsigned long long bar_staged[kDepth];      // workers -> resolver: the 16 chunks of tile k are staged
     unsigned long long bar_agg[kDepth];         // publisher -> resolver: aggregate of tile k published
     unsigned long long bar_prefix[kDepth];      // resolver -> workers: copy-out records of tile k posted
     uint2 chunk[kDepth][kW];                    // worker w, tile k: {ring position, bits} of its staged chunk
@@ -106,6 +117,7 @@ struct Ctrl {
 static_assert(sizeof(Ctrl) <= kRingsBelowOffset, "the control block must fit below the first ring");
 constexpr uint32_t kCtrlS = kSmemReserved + kCtrlOffset;
 constexpr uint32_t kBarSumsS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_sums);
+constexpr uint32_t kBarStagedS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_staged);
 constexpr uint32_t kBarAggS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_agg);
 constexpr uint32_t kBarPrefixS = kCtrlS + (uint32_t)offsetof(Ctrl, bar_prefix);
 constexpr uint32_t kChunkS = kCtrlS + (uint32_t)offsetof(Ctrl, chunk);
@@ -167,7 +179,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity)
             : "r"(bar_s), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(200);               // a blocked warp must not compete for issue slots
+        __nanosleep(HB_WAIT_NS);        // a blocked warp must not compete for issue slots
     }
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar_s, uint32_t parity)
@@ -442,8 +454,6 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
         // this warp's next tile: its tail symbols have two tiles to land
         const uint32_t sym_next = tail_symbol(k + 2u);
         long long t0 = prof.now();
-        mbar_wait(kBarAggS + slot * 8u, par_of(k));
-        prof.add(kProfWaitAgg, t0);
         prof.count(kProfTiles);
 
         // ---------------- look-back: the <= log2(n) tree nodes that tile the prefix [0, tile) ----------------
@@ -463,7 +473,7 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
                 }
                 prof.count(kProfPolls);
                 if (!__any_sync(0xFFFFFFFFu, pending)) break;
-                __nanosleep(400);
+                __nanosleep(HB_POLL_NS);
             }
             v &= kTreeSumMask;
 #pragma unroll
@@ -498,6 +508,12 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
         }
 
         // ---------------- the 16 copy-out records ----------------
+        // the look-back needed nothing from this CTA; the records need the tile's counts (which the publisher must
+        // have consumed before the slot can be reused) and its staged words
+        t0 = prof.now();
+        mbar_wait(kBarAggS + slot * 8u, par_of(k));
+        mbar_wait(kBarStagedS + slot * 8u, par_of(k));
+        prof.add(kProfWaitAgg, t0);
         const uint2 ch = lds_u64(kChunkS + (slot * kW + wk) * 8u);        // {ring position, bits}
         const uint32_t n = ch.y;
         uint32_t incl = n;
@@ -573,8 +589,8 @@ __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t ring_s, uint32_
             c1 = lds_free(a + kRow);
             b1 = lds_free(b + kRow);
         }
-        o[0] = __funnelshift_r(c0, b0, sh);
-        if (two) o[32] = __funnelshift_r(c1, b1, sh);
+        __stcs(o, __funnelshift_r(c0, b0, sh));                   // written once, never read here: stream it
+        if (two) __stcs(o + 32, __funnelshift_r(c1, b1, sh));
     }
 }
 
@@ -733,6 +749,12 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
             retire();
         }
         const uint32_t i0 = head & kRingMask;                  // the chunk's first word in the ring
+        // the count is all the look-back chain needs: post it before pass 2, so that nothing that happens to one
+        // warp while it stages (a redone lane, a late store) delays the offsets of every later tile on the GPU
+        if (lane == 0) {
+            sts_u64(my_chunk_s + slot * (kW * 8u), head, n);
+            mbar_arrive(kBarSumsS + slot * 8u);
+        }
 
         // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
         // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
@@ -812,11 +834,8 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         __syncwarp();
         prof.add(kProfEmit, t0);
 
-        // ---------------- the chunk is staged: post {ring position, bits} ----------------
-        if (lane == 0) {
-            sts_u64(my_chunk_s + slot * (kW * 8u), head, n);
-            mbar_arrive(kBarSumsS + slot * 8u);
-        }
+        // ---------------- the chunk is staged ----------------
+        if (lane == 0) mbar_arrive(kBarStagedS + slot * 8u);
         head += need;
         emitted++;
 
@@ -864,6 +883,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     if (tid == 0) {
         for (uint32_t i = 0; i < (uint32_t)kDepth; i++) {
             mbar_init(kBarSumsS + i * 8u, kW);
+            mbar_init(kBarStagedS + i * 8u, kW);
             mbar_init(kBarAggS + i * 8u, 1);
             mbar_init(kBarPrefixS + i * 8u, 1);
         }

@@ -40,7 +40,7 @@ struct EncParams {
     const uint32_t *table;            // packed: uint32[256]; wide: uint2[256] as uint32[512]
     EncResult *result;
     unsigned long long *prof;         // optional cycle counters ($HB_PROFILE), else nullptr
-    uint32_t l2_prefetch;             // pull the tile after next into L2 ($HB_L2_PREFETCH=1; off by default)
+    uint32_t l2_prefetch;             // pull the tile after next into L2 (on by default; $HB_L2_PREFETCH=0)
 };
 
 // Encode kernel variants.
