@@ -260,8 +260,9 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     if (getenv("HB_PROFILE")) {
-        ok = ok && cudaMalloc(&ctx->d_prof, 32 * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMemset(ctx->d_prof, 0, 32 * sizeof(unsigned long long)) == cudaSuccess;
+        // 32 global counters, then per worker index: cycles spent waiting for records, and the worker's total
+        ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512) * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(ctx->d_prof, 0, (32 + 512) * sizeof(unsigned long long)) == cudaSuccess;
     }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
@@ -283,11 +284,16 @@ void hb_free(hb_ctx *ctx)
         static const char *names[] = {"w0_wait_tile", "w0_wait_prefix", "w0_total", "(unused)", "rs_wait_agg",
                                       "rs_lookback", "rs_bits_before", "rs_total", "tiles", "lookback_polls",
                                       "w0_pass1", "w0_emit", "w0_copy"};
-        unsigned long long v[32];
+        unsigned long long v[32 + 512];
         if (cudaMemcpy(v, ctx->d_prof, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) {
             const double tiles = v[8] ? (double)v[8] : 1.0;
             for (int i = 0; i < 13; i++)
                 fprintf(stderr, "hb_prof %-16s %14llu  per tile %10.1f\n", names[i], v[i], (double)v[i] / tiles);
+            // share of its time each worker warp waited for records (the global counters above then sum all 16 workers)
+            fprintf(stderr, "hb_prof per-worker wait share (%%), all CTAs:");
+            for (int b = 0; b < 16; b++)
+                fprintf(stderr, "%s%3.0f", (b % 37) ? " " : "\n  ", v[32 + 256 + b] ? 100.0 * (double)v[32 + b] / (double)v[32 + 256 + b] : 0.0);
+            fprintf(stderr, "\n");
         }
         cudaFree(ctx->d_prof);
     }

@@ -152,6 +152,7 @@ struct RingCursor {
     __device__ __forceinline__ RingCursor(uint32_t ring_s, uint32_t idx) : v(SWZ ? idx : ring_s + idx * 4u) {}
     __device__ __forceinline__ uint32_t addr(uint32_t ring_s) const { return SWZ ? ring_at<true>(ring_s, v) : v; }
     __device__ __forceinline__ void next() { v += SWZ ? 1u : 4u; }
+    __device__ __forceinline__ void skip(uint32_t words) { v += SWZ ? words : 4u * words; }
 };
 
 // ---- small PTX helpers --------------------------------------------------------------------------
@@ -290,9 +291,14 @@ struct Prof {
     __device__ __forceinline__ void count(int i) { v[i]++; }
     __device__ void flush(const EncParams &p, uint32_t lane)
     {
-        if (on && lane == 0)
+        if (on && lane == 0) {
             for (int i = 0; i < kProfCount; i++)
                 if (v[i]) atomicAdd(&p.prof[i], v[i]);
+            if (v[kProfWorker]) {                              // a worker: per worker index, over all CTAs
+                atomicAdd(&p.prof[32 + (threadIdx.x >> 5)], v[kProfWaitPrefix]);
+                atomicAdd(&p.prof[32 + 256 + (threadIdx.x >> 5)], v[kProfWorker]);
+            }
+        }
     }
 };
 #else
@@ -626,6 +632,60 @@ __device__ __forceinline__ void copy_out(const EncParams &p, uint32_t ring_s, ui
     }
 }
 
+// ---- worker: one lane of a chunk, symbol by symbol ---------------------------------------------------------
+// For lanes in which a group of G codewords does not fit the 32-bit window: a single codeword (< 32 bits) always
+// does.  The lane's input registers already hold the next chunk, so its words are read again (L2, then L1).  A rolled
+// loop on purpose: rare (about 1 % of the chunks at G = 4 on the H 2.2 inputs), and as 64 unrolled symbols in the
+// middle of the worker loop it cost the common path registers and instruction-cache locality (measured: 4-9 %).
+// in/out: q = bit position, wa = ring cursor, lo_prev = window
+template <bool WIDE, bool SWZ>
+__device__ __forceinline__ void redo_lane(const uint32_t *src, uint32_t laneoff, uint32_t ring_s,
+                                          RingCursor<SWZ> &wa, uint32_t &q, uint32_t &lo_prev)
+{
+#pragma unroll 1
+    for (int wi = 0; wi < kLaneWords; wi++) {
+        const uint32_t wv = __ldg(src + wi);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t off = __byte_perm(wv, laneoff, 0x6504u | ((3u - j) << 4));
+            const uint32_t cwl = tab_ld(off);
+            const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
+            const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
+            const uint32_t qn = q + l;
+            if ((qn ^ q) & 32u) {
+                sts_u32(wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+                wa.next();
+            }
+            q = qn;
+            lo_prev = lo_new;
+        }
+    }
+}
+
+// The same with the lane's 64 symbols unrolled (its input words fetched again in two 256-bit loads).  Measured: the
+// long-code kernels (G <= 3) are faster with this one, the others with the group-level detour in the worker.
+template <bool WIDE, bool SWZ>
+__device__ __forceinline__ void redo_lane_unrolled(const uint32_t *src, uint32_t laneoff, uint32_t ring_s,
+                                                   RingCursor<SWZ> &wa, uint32_t &q, uint32_t &lo_prev)
+{
+    uint32_t wf[kLaneWords];
+    ld_lane(src, wf);
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+        const uint32_t off = __byte_perm(wf[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
+        const uint32_t cwl = tab_ld(off);
+        const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
+        const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
+        const uint32_t qn = q + l;
+        if ((qn ^ q) & 32u) {
+            sts_u32(wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+            wa.next();
+        }
+        q = qn;
+        lo_prev = lo_new;
+    }
+}
+
 // ---- worker warp ----------------------------------------------------------------------------------------
 template <int G, bool WIDE, bool CHECK>
 __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint32_t warp, uint32_t lane,
@@ -638,7 +698,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
     const unsigned char *bytes = reinterpret_cast<const unsigned char *>(p.in);
     const unsigned long long n_bytes = p.n_words * 4ULL;
 
-    Prof prof(p, warp == 0);
+    Prof prof(p, true);
     const long long t_worker = prof.now();
 
     // this warp's chunk of tile t is chunk t * kW + warp of the input, kChunkWords words.  It is `full` when it
@@ -672,6 +732,11 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
     };
     auto wait_record = [&]() {
         const long long t0 = prof.now();
+#ifdef HB_PROFILE
+        // blocking waits that really had to wait (slot kProfWaitTile), of all blocking waits (slot 3)
+        prof.v[3]++;
+        if (!mbar_test(kBarPrefixS + slot_of(retired) * 8u, par_of(retired))) prof.v[kProfWaitTile]++;
+#endif
         mbar_wait(kBarPrefixS + slot_of(retired) * 8u, par_of(retired));
         prof.add(kProfWaitPrefix, t0);
     };
@@ -764,25 +829,58 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
             RingCursor<SWZ> wa(ring_s, i0 + (q0 >> 5));                  // the word being filled
             uint32_t q = q0;                                  // chunk-relative bit position (the only serial chain)
             uint32_t lo_prev = 0;
-            if (CHECK && (ormask & ~31u)) {
-                // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one
-                // symbol at a time -- a single codeword (< 32 bits) always fits.  `w` already belongs to the next
-                // chunk, so the lane's symbols are read again.
-                uint32_t wf[kLaneWords];
-                ld_lane(src, wf);
+            if (CHECK && G <= 3 && (ormask & ~31u)) {
+                // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one symbol
+                // at a time -- a single codeword (< 32 bits) always fits
+                redo_lane_unrolled<WIDE, SWZ>(src, laneoff, ring_s, wa, q, lo_prev);
+            } else if (CHECK && (ormask & ~31u)) {
+                // A group of this lane does not fit the 32-bit window (rare, divergent; about 1 % of the chunks at
+                // G = 4 on the H 2.2 inputs -- but every late warp holds back the offsets of all later tiles, so the
+                // detour is kept short).  The snapshot after such a group is still the right window; only the words
+                // that complete INSIDE the group cannot be rebuilt from snapshots.  So: the normal pass skips them,
+                // and the group is then re-encoded symbol by symbol from its (L2-resident) input bytes.
+                uint32_t og = 0, nov = 0;
 #pragma unroll
-                for (int i = 0; i < S; i++) {
-                    const uint32_t off = __byte_perm(wf[i >> 2], laneoff, 0x6504u | ((3u - (i & 3)) << 4));
-                    const uint32_t cwl = tab_ld(off);
-                    const uint32_t l = WIDE ? tab_ld_len(off) : (cwl & 0xFFu);
-                    const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
-                    const uint32_t qn = q + l;
-                    if ((qn ^ q) & 32u) {
-                        sts_u32(wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
-                        wa.next();
+                for (int g = 0; g < NG; g++)
+                    if (gss[g] & ~31u) {
+                        og = (uint32_t)g;
+                        nov++;
                     }
-                    q = qn;
-                    lo_prev = lo_new;
+                if (nov > 1u) {
+                    redo_lane<WIDE, SWZ>(src, laneoff, ring_s, wa, q, lo_prev);      // (rarer still)
+                } else {
+                    uint32_t q_s = 0, lo_s = 0;
+                    RingCursor<SWZ> wa_s = wa;
+#pragma unroll
+                    for (int g = 0; g < NG; g++) {
+                        const uint32_t qn = q + gss[g];
+                        if ((uint32_t)g == og) {
+                            q_s = q;
+                            lo_s = lo_prev;
+                            wa_s = wa;
+                            wa.skip((qn >> 5) - (q >> 5));
+                        } else if ((qn ^ q) & 32u) {
+                            const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);
+                            sts_u32(wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
+                            wa.next();
+                        }
+                        q = qn;
+                        lo_prev = los[g];
+                    }
+                    const unsigned char *lane_bytes = reinterpret_cast<const unsigned char *>(src);
+#pragma unroll 1
+                    for (uint32_t i = og * (uint32_t)G; i < og * (uint32_t)G + (uint32_t)G && i < (uint32_t)S; i++) {
+                        uint32_t cwl, l;
+                        fetch_entry<WIDE>(tab_s, lane_bytes[(i & ~3u) + (3u - (i & 3u))], lane, cwl, l);
+                        const uint32_t lo_new = __funnelshift_l(cwl, lo_s, l);
+                        const uint32_t qn = q_s + l;
+                        if ((qn ^ q_s) & 32u) {
+                            sts_u32(wa_s.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_s, 0u, l), qn));
+                            wa_s.next();
+                        }
+                        q_s = qn;
+                        lo_s = lo_new;
+                    }
                 }
             } else {
 #pragma unroll
