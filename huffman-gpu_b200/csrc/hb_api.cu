@@ -261,8 +261,8 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     if (getenv("HB_PROFILE")) {
         // 32 global counters, then per worker index: cycles spent waiting for records, and the worker's total
-        ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512) * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMemset(ctx->d_prof, 0, (32 + 512) * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512 + 1280) * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(ctx->d_prof, 0, (32 + 512 + 1280) * sizeof(unsigned long long)) == cudaSuccess;
     }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
@@ -284,7 +284,7 @@ void hb_free(hb_ctx *ctx)
         static const char *names[] = {"w0_wait_tile", "w0_wait_prefix", "w0_total", "(unused)", "rs_wait_agg",
                                       "rs_lookback", "rs_bits_before", "rs_total", "tiles", "lookback_polls",
                                       "w0_pass1", "w0_emit", "w0_copy"};
-        unsigned long long v[32 + 512];
+        static unsigned long long v[32 + 512 + 1280];
         if (cudaMemcpy(v, ctx->d_prof, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) {
             const double tiles = v[8] ? (double)v[8] : 1.0;
             for (int i = 0; i < 13; i++)
@@ -294,6 +294,38 @@ void hb_free(hb_ctx *ctx)
             for (int b = 0; b < 16; b++)
                 fprintf(stderr, "%s%3.0f", (b % 37) ? " " : "\n  ", v[32 + 256 + b] ? 100.0 * (double)v[32 + b] / (double)v[32 + 256 + b] : 0.0);
             fprintf(stderr, "\n");
+            if (getenv("HB_PROFILE_SKEW")) {
+                static const char *what[] = {"pass 1", "scan + pass 2 (+ waits for ring space)", "copy-out", "waits for records"};
+                for (int c = 0; c < 4; c++) {
+                    fprintf(stderr, "hb_prof worker 0, kilocycles in %s, per CTA (last launch):", what[c]);
+                    for (int b = 0; b < ctx->sm_count && b < 160; b++)
+                        fprintf(stderr, "%s%4.0f", (b % 37) ? " " : "\n   ", (double)v[32 + 512 + 640 + c * 160 + b] * 1e-3);
+                    fprintf(stderr, "\n");
+                }
+            }
+            // skew between CTAs: when each published its tile at 1/4, 1/2, 3/4 and the end of its sequence
+            for (int c = 0; c < 4; c++) {
+                unsigned long long lo = ~0ULL, hi = 0;
+                for (int b = 0; b < ctx->sm_count && b < 160; b++) {
+                    const unsigned long long t = v[32 + 512 + c * 160 + b];
+                    if (t && t < lo) lo = t;
+                    if (t > hi) hi = t;
+                }
+                fprintf(stderr, "hb_prof publish skew at %d/4 of the run: %.2f us between first and last CTA\n", c + 1,
+                        hi ? (double)(hi - lo) * 1e-3 : 0.0);
+                if (getenv("HB_PROFILE_SKEW")) {
+                    if (c == 0) {
+                        fprintf(stderr, "  SM id, per CTA:");
+                        for (int b = 0; b < ctx->sm_count && b < 160; b++)
+                            fprintf(stderr, "%s%3llu", (b % 37) ? " " : "\n   ", v[32 + 256 + 64 + b]);
+                        fprintf(stderr, "\n");
+                    }
+                    fprintf(stderr, "  lag behind the first CTA (us), per CTA:");
+                    for (int b = 0; b < ctx->sm_count && b < 160; b++)
+                        fprintf(stderr, "%s%3.0f", (b % 37) ? " " : "\n   ", (double)(v[32 + 512 + c * 160 + b] - lo) * 1e-3);
+                    fprintf(stderr, "\n");
+                }
+            }
         }
         cudaFree(ctx->d_prof);
     }

@@ -59,6 +59,9 @@
 #define HB_POLL_NS 400
 #endif
 
+#define HB_LIKELY(x) __builtin_expect(!!(x), 1)
+#define HB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 namespace hb {
 namespace {
 
@@ -294,6 +297,12 @@ struct Prof {
         if (on && lane == 0) {
             for (int i = 0; i < kProfCount; i++)
                 if (v[i]) atomicAdd(&p.prof[i], v[i]);
+            if (v[kProfWorker] && threadIdx.x == 0 && blockIdx.x < 160) {      // worker 0: per CTA
+                p.prof[32 + 512 + 640 + blockIdx.x] = v[kProfPass1];
+                p.prof[32 + 512 + 640 + 160 + blockIdx.x] = v[kProfEmit];
+                p.prof[32 + 512 + 640 + 320 + blockIdx.x] = v[kProfCopy];
+                p.prof[32 + 512 + 640 + 480 + blockIdx.x] = v[kProfWaitPrefix];
+            }
             if (v[kProfWorker]) {                              // a worker: per worker index, over all CTAs
                 atomicAdd(&p.prof[32 + (threadIdx.x >> 5)], v[kProfWaitPrefix]);
                 atomicAdd(&p.prof[32 + 256 + (threadIdx.x >> 5)], v[kProfWorker]);
@@ -427,6 +436,22 @@ __device__ void publisher(const EncParams &p, uint32_t lane, uint32_t K)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(kBarAggS + slot * 8u);
+#ifdef HB_PROFILE
+        // when did this CTA publish its tile K/4, K/2, 3K/4, K-1?  (skew between CTAs, in ns of the global timer)
+        if (p.prof != nullptr && lane == 0 && blockIdx.x < 160) {
+            for (uint32_t c = 0; c < 4u; c++)
+                if (k == ((c + 1u) * K) / 4u - 1u) {
+                    unsigned long long t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    p.prof[32 + 512 + c * 160 + blockIdx.x] = t;
+                    if (c == 0) {
+                        uint32_t smid;
+                        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                        p.prof[32 + 256 + 64 + blockIdx.x] = smid;     // (slots 32+320.. are free: workers use 32+256+[0,16))
+                    }
+                }
+        }
+#endif
     }
 }
 
@@ -609,7 +634,7 @@ __device__ __forceinline__ void copy_out(const EncParams &p, uint32_t ring_s, ui
     const uint32_t sh = rec.w & 31u;
     const uint32_t nfull = (sh + n) >> 5;                      // words whose last bit is ours (<= ceil(n/32))
     const unsigned long long g0 = (unsigned long long)rec.y << 32 | rec.x;
-    if (!(rec.w & kRecSlow)) {
+    if (HB_LIKELY(!(rec.w & kRecSlow))) {
         // common case: every word this chunk owns comes from two neighbouring staged words
         copy_run<SWZ>(p.out + g0, ring_s, i0, nfull, rec.z, sh, lane);
     } else {
@@ -752,7 +777,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         // ---------------- pass 1: look up, chain codewords, sum lengths ----------------
         uint32_t los[NG], gss[NG];
         uint32_t bt = 0, ormask = 0;
-        if (full) {
+        if (HB_LIKELY(full)) {
             uint32_t lo = 0, gs = 0;
 #pragma unroll
             for (int i = 0; i < S; i++) {
@@ -824,16 +849,32 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         // ---------------- pass 2: bits -> the ring (chunk-relative alignment) ----------------
         // fast path: a staging word has at most two owners (needs >= 32 bits from every lane)
         const bool fast = full && __all_sync(0xFFFFFFFFu, bt >= 32u);
-        if (fast) {
+        if (HB_LIKELY(fast)) {
             const uint32_t wa0 = ring_at<SWZ>(ring_s, i0 + (q0 >> 5));   // the word this lane starts in
             RingCursor<SWZ> wa(ring_s, i0 + (q0 >> 5));                  // the word being filled
             uint32_t q = q0;                                  // chunk-relative bit position (the only serial chain)
             uint32_t lo_prev = 0;
-            if (CHECK && G <= 3 && (ormask & ~31u)) {
+            const bool over = CHECK && (ormask & ~31u) != 0u;     // a group of this lane is 32 bits or more
+            if (HB_LIKELY(!over)) {
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    // a group is < 32 bits: it completes at most one word, and does so iff bit 5 of q flips
+                    const uint32_t qn = q + gss[g];
+                    if ((qn ^ q) & 32u) {
+                        // the 32 bits that end at the boundary: the low (qn & 31) of them come from the window
+                        // before this group, the rest from the window after it (funnel shifts use qn mod 32)
+                        const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
+                        sts_u32(wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
+                        wa.next();
+                    }
+                    q = qn;
+                    lo_prev = los[g];
+                }
+            } else if (G <= 3) {
                 // a group of this lane does not fit the 32-bit window (rare, divergent): redo the lane one symbol
                 // at a time -- a single codeword (< 32 bits) always fits
                 redo_lane_unrolled<WIDE, SWZ>(src, laneoff, ring_s, wa, q, lo_prev);
-            } else if (CHECK && (ormask & ~31u)) {
+            } else {
                 // A group of this lane does not fit the 32-bit window (rare, divergent; about 1 % of the chunks at
                 // G = 4 on the H 2.2 inputs -- but every late warp holds back the offsets of all later tiles, so the
                 // detour is kept short).  The snapshot after such a group is still the right window; only the words
@@ -881,21 +922,6 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         q_s = qn;
                         lo_s = lo_new;
                     }
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < NG; g++) {
-                    // a group is < 32 bits: it completes at most one word, and does so iff bit 5 of q flips
-                    const uint32_t qn = q + gss[g];
-                    if ((qn ^ q) & 32u) {
-                        // the 32 bits that end at the boundary: the low (qn & 31) of them come from the window
-                        // before this group, the rest from the window after it (funnel shifts use qn mod 32)
-                        const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                        sts_u32(wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
-                        wa.next();
-                    }
-                    q = qn;
-                    lo_prev = los[g];
                 }
             }
             const uint32_t r = q & 31u;

@@ -14,7 +14,10 @@ namespace hb {
 // work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
 constexpr int kEncWorkers = 16;
 constexpr int kEncThreads = (kEncWorkers + 3) * 32;
-constexpr int kSymPerThread = 64;                                     // symbols (bytes) per lane per chunk
+#ifndef HB_SYM_PER_THREAD
+#define HB_SYM_PER_THREAD 64
+#endif
+constexpr int kSymPerThread = HB_SYM_PER_THREAD;                                     // symbols (bytes) per lane per chunk
 constexpr int kChunkBytes = 32 * kSymPerThread;                       // one warp: 2 KiB
 constexpr int kTileBytes = kEncWorkers * kChunkBytes;                 // 32 KiB
 constexpr int kTileWords = kTileBytes / 4;
