@@ -205,6 +205,35 @@ def test_every_kernel_variant_vs_oracle(hb, enc, orc, torch_mod, monkeypatch, gr
     assert len(seen) >= 2, seen
 
 
+@pytest.mark.parametrize("group", [4, 6, 8])
+@pytest.mark.parametrize("long_len", [17, 24, 31])
+def test_isolated_overlong_groups(enc, orc, torch_mod, monkeypatch, group, long_len):
+    """One over-long group (>= 32 bits) in an otherwise ordinary lane: the group-level detour of the G >= 4 kernels
+    (the normal pass skips the words completed inside the group, the group is re-encoded from its input words).
+    Bursts of 2..4 long codewords are dropped at every position of a lane, its first and last group included, sparse
+    enough that most lanes have a single such group and dense enough that some have two (the lane redo)."""
+    monkeypatch.setenv("HB_FORCE_GROUP", str(group))
+    rng = np.random.default_rng(100 * group + long_len)
+    cl = np.zeros(256, np.uint32)
+    cw = np.zeros(256, np.uint32)
+    cl[0], cw[0] = 1, 0
+    cl[1], cw[1] = 2, 0b10
+    cl[2], cw[2] = 3, 0b110
+    cl[255], cw[255] = long_len, (1 << long_len) - 2
+    cl[254], cw[254] = long_len, ((1 << long_len) - 1) & 0x55555555 | (1 << (long_len - 1))
+    n = 12 * TILE + 40
+    data = rng.choice([0, 1, 2], size=n, p=[0.6, 0.3, 0.1]).astype(np.uint8)
+    for burst in (2, 3, 4):
+        starts = rng.choice(n - 8, size=n // 400, replace=False)
+        for b in range(burst):
+            data[starts + b] = rng.choice([254, 255], size=starts.size)
+    # and the corners of a lane's 64 symbols explicitly
+    for lane_start in range(0, 6 * 64 * 32, 64 * 7):
+        data[lane_start:lane_start + 2] = 255
+        data[lane_start + 62 + 64:lane_start + 64 + 64] = 254
+    check_against_oracle(orc, enc, torch_mod, data, cw, cl)
+
+
 @pytest.mark.parametrize("max_len", [1, 5, 8, 10, 13, 16, 20, 24, 27, 31])
 def test_arbitrary_tables_lengths_0_to_31(enc, orc, torch_mod, max_len):
     """cpu_vlc_encode accepts ANY table (not only prefix codes), including zero-length symbols."""
