@@ -370,6 +370,7 @@ int hb_histogram(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t h
     HB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->d_hist, 256 * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
     HB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (hist[0] > n_words * 4ULL) return HB_ERR_STATE;       // the kernel refused its shared-memory layout (hb_misc.cu)
     return HB_OK;
 }
 

@@ -4,11 +4,13 @@
  * Histogram: replaces histo_kernel (hist.cu:34-52: one byte per load, one shared atomicAdd per
  * byte into a single 256-bin array, 2*SMs blocks) and runHisto's 32 windowed launches
  * (hist.cu:98-108, which also sample the wrong bytes -- SURVEY.md section 8 a-2).  Here: one
- * launch over the whole device-resident buffer, 128-bit streaming loads, two 1024-thread CTAs per SM, and
- * shared-memory bins laid out bins[symbol][lane]: each lane owns a column, so the 32 reductions of a warp
- * instruction always hit 32 different banks -- no serialisation however skewed the data is (measured 5.6 TB/s
- * on 1 GiB at H 2.2 and at H 7.9; per-warp bins with same-address collisions reached 2.6-3.4 TB/s).
- * 64-bit global bins.
+ * launch over the whole device-resident buffer, 128-bit streaming loads (four in flight per thread), one
+ * 1024-thread CTA per SM, and shared-memory bins laid out bins[symbol][column]: each lane owns a column, so the 32
+ * reductions of a warp instruction always hit 32 different banks -- no serialisation however skewed the data is.
+ * The bins start on a 64 KiB boundary of the shared window, so a reduction's address is one PRMT: two issue slots
+ * per byte.  Measured on 1 GiB (H 2.2 and H 7.9 alike): 5.81 TB/s = 90 % of the measured copy peak; with
+ * extract + multiply-add + RED (three slots per byte, issue slots 80 % busy) 5.57 TB/s; with per-warp bins and
+ * same-address collisions 2.6-3.4 TB/s.  64-bit global bins.
  */
 #include "hb_kernels.cuh"
 
@@ -16,30 +18,42 @@ namespace hb {
 namespace {
 
 constexpr int kHistThreads = 1024;
-constexpr int kHistUnroll = 2;                         // 128-bit loads in flight per thread
+constexpr int kHistUnroll = 4;                         // 128-bit loads in flight per thread
+// Shared-memory map of a histogram CTA (window addresses; the dynamic block starts at 0x400): the bins start on a
+// 64 KiB boundary so that ONE byte permute yields a reduction's whole address, as in the encode kernel.
+constexpr uint32_t kHistBinsWindow = 0x10000;
+constexpr uint32_t kHistReserved = 1024;
+constexpr uint32_t kHistSmemBytes = kHistBinsWindow - kHistReserved + 256u * 256u;
 
-// bins[sym][lane]: a lane only ever touches its own column, so a warp's 32 shared-memory reductions fall into 32
-// different banks whatever the data is (p(max) = 0.45 on the H 2.2 inputs: per-warp bins serialise ~14-way there).
-// Warps share the columns, hence red.shared (no return value: fire and forget) rather than plain read-modify-write.
-__device__ __forceinline__ void count_word(uint32_t col_s, uint32_t w)
+// bins[sym] is a 256-byte slot: word `lane` for even warps, word 32 + lane for odd warps.  A lane only ever touches
+// its own column, so a warp's 32 shared-memory reductions fall into 32 different banks whatever the data is
+// (p(max) = 0.45 on the H 2.2 inputs: per-warp bins serialise ~14-way there).  Warps share the columns, hence
+// red.shared (no return value: fire and forget) rather than a plain read-modify-write.  Two issue slots per byte:
+// PRMT {column offset, symbol, 0x01, 0x00} -> address, RED.
+__device__ __forceinline__ void count_word(uint32_t col, uint32_t w)
 {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const uint32_t sym = (w >> (8 * k)) & 0xFFu;
-        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(col_s + sym * 128u) : "memory");
-    }
+    for (int k = 0; k < 4; k++)
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(__byte_perm(w, col, 0x6504u | (uint32_t)k << 4)) : "memory");
 }
 
-__global__ void __launch_bounds__(kHistThreads, 2) hist_kernel(const uint32_t *__restrict__ in,
+__global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const uint32_t *__restrict__ in,
                                                                unsigned long long n_words,
                                                                unsigned long long *__restrict__ hist)
 {
-    __shared__ uint32_t bins[256 * 32];
+    extern __shared__ __align__(1024) uint32_t hist_smem[];
+    uint32_t *bins = hist_smem + (kHistBinsWindow - kHistReserved) / 4;
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i < 256u * 32u; i += kHistThreads) bins[i] = 0u;
+    if ((uint32_t)__cvta_generic_to_shared(bins) != kHistBinsWindow) {
+        // the shared window is not laid out as assumed: refuse loudly (the host checks this bin) instead of miscounting
+        if (tid == 0 && blockIdx.x == 0) atomicAdd(&hist[0], ~0ULL >> 1);
+        return;
+    }
+    for (uint32_t i = tid; i < 256u * 64u; i += kHistThreads) bins[i] = 0u;
     __syncthreads();
 
-    const uint32_t col_s = (uint32_t)__cvta_generic_to_shared(bins) + (tid & 31u) * 4u;
+    // prmt source b: byte 0 = column offset inside a slot, bytes 1..2 = bytes 2..3 of the bins' window address
+    const uint32_t col = ((tid & 31u) * 4u + ((tid >> 5) & 1u) * 128u) | ((kHistBinsWindow >> 16) << 8);
     const unsigned long long gtid = (unsigned long long)blockIdx.x * kHistThreads + tid;
     const unsigned long long stride = (unsigned long long)gridDim.x * kHistThreads;
 
@@ -61,24 +75,24 @@ __global__ void __launch_bounds__(kHistThreads, 2) hist_kernel(const uint32_t *_
 #pragma unroll
         for (int u = 0; u < kHistUnroll; u++) {
             if (i + (unsigned long long)u * stride < n_vec) {
-                count_word(col_s, v[u].x);
-                count_word(col_s, v[u].y);
-                count_word(col_s, v[u].z);
-                count_word(col_s, v[u].w);
+                count_word(col, v[u].x);
+                count_word(col, v[u].y);
+                count_word(col, v[u].z);
+                count_word(col, v[u].w);
             }
         }
     }
     const unsigned long long rest0 = head + n_vec * 4;
-    if (gtid < head) count_word(col_s, in[gtid]);
-    if (gtid < n_words - rest0) count_word(col_s, in[rest0 + gtid]);
+    if (gtid < head) count_word(col, in[gtid]);
+    if (gtid < n_words - rest0) count_word(col, in[rest0 + gtid]);
     __syncthreads();
 
-    // 4 threads per symbol, 8 columns each
+    // 4 threads per symbol, 16 columns each
     {
         const uint32_t sym = tid >> 2, part = tid & 3u;
         unsigned long long sum = 0;
 #pragma unroll
-        for (int c = 0; c < 8; c++) sum += bins[sym * 32u + part * 8u + c];
+        for (int c = 0; c < 16; c++) sum += bins[sym * 64u + part * 16u + c];
         sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 1);
         sum += __shfl_xor_sync(0xFFFFFFFFu, sum, 2);
         if (part == 0 && sum) atomicAdd(&hist[sym], sum);
@@ -146,13 +160,21 @@ cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
                              unsigned long long *d_hist, int sm_count, cudaStream_t stream)
 {
     if (n_words == 0) return cudaSuccess;
-    // two CTAs of 1024 threads per SM (32 KiB of bins each), kHistUnroll 128-bit loads per thread and trip
+    // one CTA of 1024 threads per SM (its 64 KiB of bins sit on a 64 KiB boundary of the shared window),
+    // kHistUnroll 128-bit loads per thread and trip
+    static bool configured = false;
+    if (!configured) {
+        const cudaError_t e = cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)kHistSmemBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     unsigned long long want = (n_words / 4 + (unsigned long long)kHistThreads * kHistUnroll - 1) /
                               ((unsigned long long)kHistThreads * kHistUnroll);
     if (want < 1) want = 1;
-    const unsigned long long cap = (unsigned long long)sm_count * 2;
+    const unsigned long long cap = (unsigned long long)sm_count;
     const int grid = (int)(want < cap ? want : cap);
-    hist_kernel<<<grid, kHistThreads, 0, stream>>>(d_in, n_words, d_hist);
+    hist_kernel<<<grid, kHistThreads, kHistSmemBytes, stream>>>(d_in, n_words, d_hist);
     return cudaGetLastError();
 }
 
