@@ -261,8 +261,8 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
     if (getenv("HB_PROFILE")) {
         // 32 global counters, then per worker index: cycles spent waiting for records, and the worker's total
-        ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512 + 1280) * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMemset(ctx->d_prof, 0, (32 + 512 + 1280) * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512 + 1280 + 960) * sizeof(unsigned long long)) == cudaSuccess;
+        ok = ok && cudaMemset(ctx->d_prof, 0, (32 + 512 + 1280 + 960) * sizeof(unsigned long long)) == cudaSuccess;
     }
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) {
@@ -284,7 +284,7 @@ void hb_free(hb_ctx *ctx)
         static const char *names[] = {"w0_wait_tile", "w0_wait_prefix", "w0_total", "(unused)", "rs_wait_agg",
                                       "rs_lookback", "rs_bits_before", "rs_total", "tiles", "lookback_polls",
                                       "w0_pass1", "w0_emit", "w0_copy"};
-        static unsigned long long v[32 + 512 + 1280];
+        static unsigned long long v[32 + 512 + 1280 + 960];
         if (cudaMemcpy(v, ctx->d_prof, sizeof(v), cudaMemcpyDeviceToHost) == cudaSuccess) {
             const double tiles = v[8] ? (double)v[8] : 1.0;
             for (int i = 0; i < 13; i++)
@@ -301,6 +301,25 @@ void hb_free(hb_ctx *ctx)
                     for (int b = 0; b < ctx->sm_count && b < 160; b++)
                         fprintf(stderr, "%s%4.0f", (b % 37) ? " " : "\n   ", (double)v[32 + 512 + 640 + c * 160 + b] * 1e-3);
                     fprintf(stderr, "\n");
+                }
+            }
+            {
+                // timeline of the last launch, relative to the first CTA's entry (global timer)
+                static const char *stage[] = {"kernel entry", "prologue done", "first tile published", "last tile published",
+                                              "worker 0 encoded its last chunk", "worker 0 copied its last chunk out"};
+                unsigned long long t0 = ~0ULL;
+                for (int b = 0; b < ctx->sm_count && b < 160; b++)
+                    if (v[32 + 512 + 1280 + b] && v[32 + 512 + 1280 + b] < t0) t0 = v[32 + 512 + 1280 + b];
+                for (int c = 0; c < 6; c++) {
+                    unsigned long long lo = ~0ULL, hi = 0;
+                    for (int b = 0; b < ctx->sm_count && b < 160; b++) {
+                        const unsigned long long t = v[32 + 512 + 1280 + c * 160 + b];
+                        if (t && t < lo) lo = t;
+                        if (t > hi) hi = t;
+                    }
+                    if (hi)
+                        fprintf(stderr, "hb_prof timeline %-36s first CTA %8.2f us, last CTA %8.2f us\n", stage[c],
+                                (double)(lo - t0) * 1e-3, (double)(hi - t0) * 1e-3);
                 }
             }
             // skew between CTAs: when each published its tile at 1/4, 1/2, 3/4 and the end of its sequence

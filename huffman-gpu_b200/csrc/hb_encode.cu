@@ -320,6 +320,21 @@ struct Prof {
 };
 #endif
 
+#ifdef HB_PROFILE
+// launch timeline (global timer, ns): prof[32 + 512 + 1280 + stage * 160 + CTA]
+__device__ __forceinline__ void stamp(const EncParams &p, uint32_t stage)
+{
+    if (p.prof != nullptr && blockIdx.x < 160) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.prof[32 + 512 + 1280 + stage * 160 + blockIdx.x] = t;
+    }
+}
+#define HB_STAMP(p, stage, cond) do { if (cond) stamp(p, stage); } while (0)
+#else
+#define HB_STAMP(p, stage, cond) do { } while (0)
+#endif
+
 // ---- codebook in shared memory ---------------------------------------------------------------------
 // slot(sym) = 256 bytes: words 0..31 = the entry replicated per lane; wide tables keep the length in
 // words 32..63.  Lookups take a complete shared-window address (table base + sym*256 + lane*4).
@@ -436,6 +451,8 @@ __device__ void publisher(const EncParams &p, uint32_t lane, uint32_t K)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(kBarAggS + slot * 8u);
+        HB_STAMP(p, 2, lane == 0 && k == 0);
+        HB_STAMP(p, 3, lane == 0 && k + 1 == K);
 #ifdef HB_PROFILE
         // when did this CTA publish its tile K/4, K/2, 3K/4, K-1?  (skew between CTAs, in ns of the global timer)
         if (p.prof != nullptr && lane == 0 && blockIdx.x < 160) {
@@ -973,10 +990,12 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         if (ready) retire();
         src += step;
     }
+    HB_STAMP(p, 4, warp == 0 && lane == 0);
     while (retired < emitted) {
         wait_record();
         retire();
     }
+    HB_STAMP(p, 5, warp == 0 && lane == 0);
     prof.add(kProfWorker, t_worker);
     prof.flush(p, lane);
 }
@@ -998,7 +1017,19 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31u;
     const uint32_t warp = tid >> 5;
+    HB_STAMP(p, 0, tid == 0);
 
+    // the CTA's first two tiles start their way from DRAM to L2 while the prologue runs (a worker's chunk of tile t
+    // is chunk t * kW + warp; a lane touches 64 bytes of it)
+    if (p.l2_prefetch && warp < (uint32_t)kW) {
+#pragma unroll
+        for (uint32_t j = 0; j < 2u; j++) {
+            const unsigned long long t = p.first_tile + blockIdx.x + (unsigned long long)j * gridDim.x;
+            if (t < p.end_tile && (t * kW + warp + 1ULL) * (unsigned long long)kChunkWords <= p.n_words)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.in + (t * kW + warp) * (unsigned long long)kChunkWords +
+                                                             lane * (uint32_t)kLaneWords));
+        }
+    }
     // the tree the NEXT job on this context will use (nothing reads or writes it during this launch)
     for (unsigned long long i = (unsigned long long)blockIdx.x * kEncThreads + tid; i < p.zero_count;
          i += (unsigned long long)gridDim.x * kEncThreads)
@@ -1013,6 +1044,7 @@ __global__ void __launch_bounds__(kEncThreads, 1) encode_kernel(const EncParams 
         }
     }
     __syncthreads();
+    HB_STAMP(p, 1, tid == 0);
 
     // CTA b takes tiles first_tile + b, + grid, + 2 grid, ...: K of them (the grid never exceeds the tile count)
     const unsigned long long span = p.end_tile - p.first_tile;
