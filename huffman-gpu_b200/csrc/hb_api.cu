@@ -232,6 +232,7 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
     if (e == cudaSuccess && prop.major < 10) e = cudaErrorNoKernelImageForDevice;   // sm_100a only
     if (e == cudaSuccess) e = hb::encode_configure();
+    if (e == cudaSuccess) e = hb::histogram_configure();
     if (e != cudaSuccess) {
         int rc = cuda_fail(ctx, e);
         fprintf(stderr, "hb_init: CUDA error %d (%s); libhuffb200 has no CPU fallback\n", (int)e,

@@ -66,6 +66,7 @@ size_t encode_smem_bytes(const EncVariant &v);
 cudaError_t encode_configure();                        // opt-in smem attributes, once per process
 cudaError_t launch_encode(const EncVariant &v, const EncParams &p, int grid, cudaStream_t stream);
 
+cudaError_t histogram_configure();                     // opt-in smem attribute, once per device context
 cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
                              unsigned long long *d_hist, int sm_count, cudaStream_t stream);
 cudaError_t launch_or_words(uint32_t *d_dst, const uint32_t *d_src, unsigned long long n_words,

@@ -156,19 +156,17 @@ __global__ void __launch_bounds__(256) synth_kernel(uint8_t *out, unsigned long 
 
 }  // namespace
 
+cudaError_t histogram_configure()
+{
+    return cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHistSmemBytes);
+}
+
 cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
                              unsigned long long *d_hist, int sm_count, cudaStream_t stream)
 {
     if (n_words == 0) return cudaSuccess;
     // one CTA of 1024 threads per SM (its 64 KiB of bins sit on a 64 KiB boundary of the shared window),
     // kHistUnroll 128-bit loads per thread and trip
-    static bool configured = false;
-    if (!configured) {
-        const cudaError_t e = cudaFuncSetAttribute(hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)kHistSmemBytes);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
     unsigned long long want = (n_words / 4 + (unsigned long long)kHistThreads * kHistUnroll - 1) /
                               ((unsigned long long)kHistThreads * kHistUnroll);
     if (want < 1) want = 1;

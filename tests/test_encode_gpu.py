@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle / the unmodified
 reference / the committed golden vectors.  Bit-exact: this is integer work, tolerance zero.
 Run on the B200 box with `pytest -m gpu`."""
+import os
+
 import numpy as np
 import pytest
 
@@ -498,3 +500,21 @@ def test_reference_gpu_pipeline_agrees_on_fixture(hb, enc, orc, torch_mod, c1):
     ref_words = d_ref.cpu().numpy().view(np.uint32)[:nw]
     assert our_bits == bits and np.array_equal(ref_words, ours[:nw])
     assert orc.word_fnv(ref_words) == c1["fnv"]
+
+
+def test_cli_driver_on_the_fixture_and_a_ragged_file(hb, tmp_path):
+    """pavle_b200 <file>: the reference driver's sequence and output fields (main_test_cu.cu:41-180); PASS! means the
+    bit count equals sum(hist * len) and the GPU stream decodes back to the file."""
+    import subprocess
+    cli = os.path.join(os.path.dirname(hb.capi.LIB_PATH), "pavle_b200")
+    fixture = tmp_path / "test1024.in"
+    fixture.write_bytes(hb.workloads.c1_fixture_bytes().tobytes())
+    out = subprocess.run([cli, str(fixture)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "GPU Encoded to 291334 [B]" in out.stdout and "PASS!" in out.stdout       # SURVEY section 8c golden value
+    assert "entropy 2.2065" in out.stdout
+    rng = np.random.default_rng(7)
+    ragged = tmp_path / "ragged.in"
+    ragged.write_bytes(rng.choice(256, size=3 * TILE + 4 * 37 + 3, p=np.r_[0.7, np.full(255, 0.3 / 255)]).astype(np.uint8).tobytes())
+    out = subprocess.run([cli, str(ragged), "--repeats", "3"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "PASS!" in out.stdout, out.stdout + out.stderr

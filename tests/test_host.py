@@ -44,6 +44,21 @@ def test_no_cpu_fallback_without_gpu(hb):
                       np.ones(256, np.uint32))
 
 
+def test_cli_driver_builds_and_fails_loudly_without_gpu(hb, tmp_path):
+    """pavle_b200 (the reference's command-line driver on top of the C ABI)"""
+    import subprocess
+    import torch
+    cli = os.path.join(ROOT, "huffman-gpu_b200", "pavle_b200")
+    assert os.path.exists(cli), "the driver is built by `make -C huffman-gpu_b200/csrc`"
+    out = subprocess.run([cli], capture_output=True, text=True)
+    assert out.returncode == 2 and "No input file" in out.stdout           # load_data.h:27
+    if not torch.cuda.is_available():
+        p = tmp_path / "x.in"
+        p.write_bytes(bytes(range(256)) * 16)
+        out = subprocess.run([cli, str(p)], capture_output=True, text=True)
+        assert out.returncode == 3 and "PASS" not in out.stdout              # no device: no fallback, no verdict
+
+
 def test_product_never_references_oracle():
     """the product path may not import/link/execute anything under oracle/"""
     pkg = os.path.join(ROOT, "huffman-gpu_b200")
