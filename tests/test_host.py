@@ -145,3 +145,18 @@ def test_workload_thresholds(hb):
         assert w.thr[-1] == 0xFFFFFFFF
     w = hb.workloads.get("c2", n_bytes=4096)
     assert w.n_words == 1024
+
+
+def test_stats_series_sink_format(hb, tmp_path):
+    """stats_logger's file format (stats_logger.cpp:13-44): header once, then one "x y" line per sample; LogStats2
+    also derives the data-rate series MB * 1000 / (ms * 1024)."""
+    d = str(tmp_path)
+    hb.stats.log_stats2(d, "encode_t", "B200", 2.0, 256.0, series_number=3, description="d")
+    hb.stats.log_stats2(d, "encode_t", "B200", 4.0, 1024.0)
+    lines = open(os.path.join(d, "encode_t__3_B200.txt")).read().splitlines()
+    assert lines[:16] == ["SERIES_NAME", "B200", "X_AXIS_QUANTITY", "Data size", "Y_AXIS_QUANTITY", "Time",
+                          "X_AXIS_UNIT", "MB", "Y_AXIS_UNIT", "ms", "X_AXIS_SCALE_TYPE", "log",
+                          "Y_AXIS_SCALE_TYPE", "lin", "DESCRIPTION", "d"]
+    assert lines[16:] == ["__DATA__", "256.000000 2.000000", "1024.000000 4.000000"]
+    rate = open(os.path.join(d, "encode_t_datarate__3_B200.txt")).read().splitlines()
+    assert rate[-2:] == ["256.000000 125.000000", "1024.000000 250.000000"] and "GB/s" in rate
