@@ -54,7 +54,9 @@ struct hb_ctx {
     uint64_t out_buf_words = 0;
     cudaStream_t s_main = nullptr;
     cudaStream_t s_d2h = nullptr;
+    cudaStream_t s_h2d = nullptr;
     cudaEvent_t ev_chunk[64] = {};            // one per launch of a chunked host job
+    cudaEvent_t ev_h2d[64] = {};              // ... and one per input copy
 
     unsigned long long *d_prof = nullptr;     // $HB_PROFILE: kernel cycle counters, dumped by hb_free
     uint64_t launches = 0;
@@ -257,9 +259,11 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     ok = ok && cudaMalloc(&ctx->d_symmap, 256) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->table_uploaded, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kMaxChunks; i++)
-        ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
     if (getenv("HB_PROFILE")) {
         // 32 global counters, then per worker index: cycles spent waiting for records, and the worker's total
         ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512 + 1280 + 960) * sizeof(unsigned long long)) == cudaSuccess;
@@ -360,10 +364,13 @@ void hb_free(hb_ctx *ctx)
     cudaFree(ctx->d_in_buf);
     cudaFree(ctx->d_out_buf);
     if (ctx->table_uploaded) cudaEventDestroy(ctx->table_uploaded);
-    for (int i = 0; i < kMaxChunks; i++)
+    for (int i = 0; i < kMaxChunks; i++) {
         if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    }
     if (ctx->s_main) cudaStreamDestroy(ctx->s_main);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     (void)cudaGetLastError();
     delete ctx;
 }
@@ -507,11 +514,13 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
         h_out[0] = 0;                          // cpuencode.cpp:17
     } else {
         next_job(ctx);
-        // Chunked: the H2D copy of chunk k+1 overlaps the encode of chunk k, and the D2H copy of the words
-        // chunk k completed overlaps both (PCIe is full duplex).  All chunks belong to ONE job (one look-back
-        // tree, one output stream); a later launch looks back into the tree nodes and symbols of the earlier ones.
+        // Chunked, three streams: the H2D copies run back to back on their own stream, the encode of chunk k (which
+        // waits for copy k only) overlaps copy k+1, and the D2H copy of the words chunk k completed overlaps both
+        // (PCIe is full duplex).  Small chunks keep the fill (first copy) and the drain (last encode + last D2H) short.
+        // All chunks belong to ONE job (one look-back tree, one output stream); a later launch looks back into the
+        // tree nodes and symbols of the earlier ones.
         const uint64_t total_tiles = tiles_of(n_words);
-        uint64_t chunk_tiles = (32ull << 20) / hb::kTileBytes;           // 32 MiB of input per chunk ...
+        uint64_t chunk_tiles = (16ull << 20) / hb::kTileBytes;           // 16 MiB of input per chunk ...
         static const char *env = getenv("HB_CHUNK_MIB");
         if (env && atoi(env) > 0) chunk_tiles = ((uint64_t)atoi(env) << 20) / hb::kTileBytes;
         if (chunk_tiles < 1) chunk_tiles = 1;
@@ -523,7 +532,9 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
             const uint64_t w0 = t0 * hb::kTileWords;
             const uint64_t w1 = (t1 * hb::kTileWords < n_words) ? t1 * hb::kTileWords : n_words;
             HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_buf + w0, h_in + w0, (w1 - w0) * sizeof(uint32_t),
-                                         cudaMemcpyHostToDevice, st));
+                                         cudaMemcpyHostToDevice, ctx->s_h2d));
+            HB_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[n_chunks], ctx->s_h2d));
+            HB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[n_chunks], 0));
             rc = launch_tiles(ctx, ctx->d_in_buf, n_words, t0, t1, ctx->d_out_buf, dev_out_words, 0, st, n_chunks);
             if (rc != HB_OK) return rc;
             HB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[n_chunks], st));
