@@ -24,7 +24,7 @@ tot = sum(a[1] for a in agg.values())
 with open(os.path.join(out, "%s_launches.txt" % tag), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (cold-cache, serialised: compare shares)\n")
     f.write("# command: python bench.py --steps 3 --warmup 3 --no-cpu   (device-resident steps, then the host-buffer e2e path\n")
-    f.write("#          whose 32 MiB chunks are separate launches of the same kernel)\n")
+    f.write("#          whose chunks (16 MiB; 32 MiB before r1d) are separate launches of the same kernel)\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("%-40s launches %3d  total %10.1f us  share %5.1f%%  avg %9.1f us\n" % (k[:40], n, t, 100 * t / tot, t / n))
     f.write("\n" + "\n".join(lines) + "\n")
