@@ -249,6 +249,7 @@ def main():
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-stitch", action="store_true", help="N > 1: skip the optional gather of the shards on rank 0")
     ap.add_argument("--e2e-steps", type=int, default=None, help="default: min(steps, 20)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -370,6 +371,30 @@ def main():
         "histogram": {"GBps": n_bytes / (hist_ms * 1e-3) / 1e9, "ms": hist_ms},
         "clocks": sampler.summary(),
     }
+
+    # ---- optional stitch (N > 1): the shards gathered on rank 0 over NVLink, seam words OR-ed; reported separately ----
+    if dist is not None and not args.no_stitch:
+        try:
+            from huffman_gpu_b200 import sharded
+            or_fn = lambda dst, src: enc.stitch_seam(dst, src, 1)          # noqa: E731
+            stitched = sharded.stitch_on_rank0(plan, d_out, or_fn=or_fn)   # warm: NCCL sets its P2P channels up lazily
+            del stitched
+            dist.barrier()
+            torch.cuda.synchronize()
+            s0 = time.perf_counter()
+            stitched = sharded.stitch_on_rank0(plan, d_out, or_fn=or_fn)
+            torch.cuda.synchronize()
+            dist.barrier()
+            st = torch.tensor([time.perf_counter() - s0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(st, op=dist.ReduceOp.MAX)
+            out_total = int(plan.total_bits) // 8
+            line["stitch"] = {"ms": float(st[0]) * 1e3, "stream_bytes": out_total,
+                              "GBps_of_stream": out_total / float(st[0]) / 1e9,
+                              "what": "NCCL send/recv of every shard's words to rank 0 + one OR per seam word; "
+                                      "not part of `value`"}
+            del stitched
+        except Exception as exc:                                   # never let the optional leg break the line
+            line["stitch"] = {"error": repr(exc)}
 
     # ---- e2e through the host-buffer C-ABI call (rank-local, wall clock, pinned host buffers) ----------------
     if not args.no_e2e:
