@@ -14,8 +14,7 @@
  *   - one persistent CTA per SM (a cooperative launch: all CTAs are co-resident): 16 autonomous WORKER
  *     warps, a PUBLISHER warp and two RESOLVER warps.  CTA b takes tiles b, b + grid, b + 2 grid, ... of
  *     32 KiB, so the tiles in flight at any time are consecutive; a worker warp owns a 2 KiB chunk of each
- *     tile, processed as two 1 KiB sub-blocks (32 contiguous symbols per lane, one 256-bit load per lane,
- *     prefetched one sub-block ahead);
+ *     tile (64 contiguous symbols per lane, two 256-bit loads per lane, requested one chunk ahead);
  *   - the codebook lives in shared memory at a 256-byte stride per symbol, replicated per lane:
  *     ONE byte-permute builds the whole lookup address (symbol -> byte 1, lane*4 -> byte 0) and
  *     the lookup is bank-conflict free for any symbol distribution.  An entry is
@@ -23,32 +22,35 @@
  *     (shf.l.wrap takes its shift count from the low 5 bits of the same register) and one dp4a
  *     accumulates the length: 4 issue slots per symbol (prmt, lds, shf, dp4a);
  *   - the window is snapshotted every G symbols.  After a warp shuffle scan has placed the lane
- *     inside the warp's chunk, a second pass over the G-symbol groups only tests "did this group
- *     cross a 32-bit word boundary" and, if so, rebuilds that word from two neighbouring
- *     snapshots with two funnel shifts and stores it to the warp's private staging region.
- *     Because every lane of a full chunk emits >= 32 bits, a staging word has at most two owners:
- *     the left lane hands its partial tail word to the right one through a shuffle -- no
- *     shared-memory atomics, no zeroing.  Chunks that break the rules (ragged end of the input,
- *     zero-length codes, a group of 32+ bits) are re-encoded symbol by symbol with atomicOr;
- *   - workers never synchronise with each other.  They post their chunk's bit count; the publisher
- *     sums the 16 counts and publishes the tile aggregate at once (it never waits on other CTAs, so
- *     there is no convoy).  Global bit offsets come from a decoupled look-back over a FENWICK TREE
- *     instead of a flat descriptor array: with 148 tiles in flight and a new tile every ~7 cycles
- *     GPU-wide, a classic look-back (every tile re-reading all of its ~148 unresolved predecessors,
- *     again on every poll) turns a handful of descriptor lines into an L2 hot spot.  Here a tile adds
- *     {1, bits} with one fire-and-forget 64-bit red.add to the <= log2(n) tree nodes that cover it,
- *     and the resolver of a later tile reads the <= log2(n) nodes that tile its prefix; a node is
- *     final when its count equals the number of tiles it covers.  O(log n) traffic per tile, no
- *     serial chain, no scanner, and nothing to reset: each job zeroes the tree of the next one;
+ *     inside the warp's chunk, the worker posts the chunk's bit count (all the look-back chain needs),
+ *     and a second pass over the G-symbol groups only tests "did this group cross a 32-bit word
+ *     boundary" and, if so, rebuilds that word from two neighbouring snapshots with two funnel shifts
+ *     and stores it to the warp's private staging ring.  Because every lane of a full chunk emits
+ *     >= 32 bits, a staging word has at most two owners: the left lane hands its partial tail word to
+ *     the right one through a shuffle -- no shared-memory atomics, no zeroing.  A group of 32+ bits
+ *     (rare) is re-encoded on its own, symbol by symbol; chunks that break the rules (ragged end of the
+ *     input, zero-length codes) are re-encoded symbol by symbol with red.shared.or;
+ *   - workers never synchronise with each other; mbarriers carry every hand-off.  The publisher sums
+ *     the 16 counts and publishes the tile aggregate at once (it never waits on other CTAs, so there is
+ *     no convoy).  Global bit offsets come from a decoupled look-back over a FENWICK TREE instead of a
+ *     flat descriptor array: with 148 tiles in flight and a new tile every ~7 cycles GPU-wide, a
+ *     classic look-back (every tile re-reading all of its ~148 unresolved predecessors, again on every
+ *     poll) turns a handful of descriptor lines into an L2 hot spot.  Here a tile adds {1, bits} with
+ *     one fire-and-forget 64-bit red.add to the <= log2(n) tree nodes that cover it, and the resolver
+ *     of a later tile reads the <= log2(n) nodes that tile its prefix; a node is final when its count
+ *     equals the number of tiles it covers.  O(log n) traffic per tile, no serial chain, no scanner,
+ *     and nothing to reset: each job zeroes the tree of the next one;
+ *   - the resolver then prepares, 16 chunks in 16 lanes, what each worker needs to copy its chunk out:
+ *     first output word, phase, and the (< 32) stream bits that precede the chunk (the left
+ *     neighbour's staged tail; for the first chunk of a tile they are re-derived from the symbols just
+ *     before the tile, so there is no inter-CTA data dependency);
  *   - all of this runs while the workers are already encoding the next tiles: a worker stages its
- *     chunks in a private shared-memory RING (9.5 KiB, allocated by actual size), so up to 8 tiles
- *     can be between encode and copy-out and the latency of the look-back -- and its variance
- *     across 148 CTAs -- never reaches the encode loop.  mbarriers carry every hand-off;
- *   - as soon as a tile's offset is resolved each worker copies its own chunk out, coalesced, with
- *     one funnel shift per word to the global phase.  An output word that straddles two chunks belongs to
- *     the right-hand chunk, which takes the missing (< 32) bits from a tiny carry ring; for the
- *     first chunk of a tile the resolver re-derives them from the symbols just before the tile,
- *     so there is no inter-CTA data dependency, no atomics on the output and no memset of it.
+ *     chunks in a private shared-memory RING (2048 words, allocated by actual size), so up to 16 tiles
+ *     (or a full ring) can be between encode and copy-out and the latency of the look-back -- and its
+ *     variance across 148 CTAs -- rarely reaches the encode loop;
+ *   - as soon as a chunk's record is there its worker copies it out, coalesced, with one funnel shift
+ *     per word to the global phase.  An output word that straddles two chunks belongs to the
+ *     right-hand chunk: no atomics on the output and no memset of it.
  */
 #include "hb_kernels.cuh"
 
@@ -81,12 +83,11 @@ constexpr unsigned long long kTreeSumMask = kTreeOne - 1ULL;
 
 // Shared-memory map (addresses in the CTA's shared WINDOW; the dynamic block starts at kSmemReserved):
 //   0x00400  control block (mbarriers, per-tile hand-off data)
-//   0x02000  staging rings of workers 0..6      (7 x 8 KiB)
+//   0x02000  staging rings of workers 0..5      (6 x 8.25 KiB: 2048 words + 64 pad words)
 //   0x10000  codebook table                      (64 KiB)
-//   0x20000  staging rings of workers 7..15     (9 x 8 KiB)
+//   0x20000  staging rings of workers 6..15     (10 x 8.25 KiB)
 // The table starts on a 64 KiB boundary so that one byte permute yields a complete lookup address (window
-// address bytes 2..3 are constants); every ring is aligned to its size so that a ring address wraps with
-// one AND/OR on the address itself.
+// address bytes 2..3 are constants).
 constexpr uint32_t kSmemReserved = 1024;                // cudaDevAttrReservedSharedMemoryPerBlock on sm_100
 constexpr uint32_t kTabWindow = 0x10000;
 constexpr uint32_t kTabOffset = kTabWindow - kSmemReserved;          // offsets are inside the dynamic block
