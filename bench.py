@@ -64,8 +64,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
-        self.reasons = set()
+        self.trace = []                       # (time, sm clock, reasons mask, inside the timed region?)
         self.sm_max = None
         self.active = threading.Event()
         self.stop_flag = threading.Event()
@@ -90,37 +89,43 @@ class ClockSampler(threading.Thread):
         return clk, mask
 
     def run(self):
+        """polls from start() to stop: every sample is time-stamped, the summary keeps those inside the timed region"""
         if not self.ok:
             return
         while not self.stop_flag.is_set():
-            if self.active.is_set():
-                try:
-                    clk, mask = self._one()
-                    self.samples.append(clk)
-                    for bit, name in self.REASONS.items():
-                        if mask & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
-            else:
-                time.sleep(0.0005)
+            try:
+                t = time.perf_counter()
+                clk, mask = self._one()
+                self.trace.append((t, clk, mask, self.active.is_set()))
+            except Exception:
+                pass
+            time.sleep(0.0002)
 
     def summary(self):
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml_unavailable"], "samples": 0}
-        tail = False
-        if not self.samples:                  # region shorter than one NVML call
+        inside = [(c, m) for (_, c, m, act) in self.trace if act]
+        note = None
+        if not inside:
+            # the region was shorter than one poll: take the polls right around it (the last before the region ended
+            # is still inside the busy phase that started with the warm-up)
+            busy = [(c, m) for (_, c, m, _) in self.trace[-3:]]
             try:
-                clk, mask = self._one()
-                self.samples.append(clk)
-                tail = True
+                busy.append(self._one())
             except Exception:
                 pass
-        med = float(np.median(self.samples)) if self.samples else None
-        out = {"sm_mhz": med, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
-               "samples": len(self.samples)}
-        if tail:
-            out["note"] = "timed region shorter than one NVML poll; sampled right after it"
+            inside = busy
+            note = "timed region shorter than one NVML poll; nearest polls around it"
+        reasons = set()
+        for _, mask in inside:
+            for bit, name in self.REASONS.items():
+                if mask & bit:
+                    reasons.add(name)
+        clocks = [c for c, _ in inside]
+        out = {"sm_mhz": float(np.median(clocks)) if clocks else None, "sm_max_mhz": self.sm_max,
+               "reasons": sorted(reasons), "samples": len(clocks)}
+        if note:
+            out["note"] = note
         return out
 
 
@@ -239,7 +244,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "t1g", "c3", "c4", "c5"])
