@@ -207,6 +207,48 @@ def test_every_kernel_variant_vs_oracle(hb, enc, orc, torch_mod, monkeypatch, gr
     assert len(seen) >= 2, seen
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_nonstationary_many_rounds(hb, enc, orc, torch_mod, seed):
+    """Ten and more tiles per CTA with chunk sizes that swing between a few words and a full ring: segments of
+    very different entropy under ONE codebook (ring wrap and skip, ring-full and depth-limit retirements, records that
+    arrive early and late), ragged end, a shard phase."""
+    rng = np.random.default_rng(1000 + seed)
+    nsym = [256, 64, 32][seed - 1]
+    h = random_prefix_code(rng, nsym, ["flat", "geo", "fib"][seed - 1])
+    cw, cl, max_len = hb.build_codebook(h)
+    syms = np.nonzero(h)[0]
+    order = syms[np.argsort(cl[syms])]                       # shortest codes first
+    parts = []
+    total = 0
+    while total < 40 * 1024 * 1024:
+        n = int(rng.integers(1, 64)) * 4096 + 4 * int(rng.integers(0, 64))
+        kind = int(rng.integers(0, 4))
+        if kind == 0:                                        # the shortest code only: a chunk of a few words
+            seg = np.full(n, order[0], dtype=np.uint8)
+        elif kind == 1:                                      # the longest codes only: the largest chunks this book allows
+            seg = rng.choice(order[-max(1, nsym // 8):], size=n).astype(np.uint8)
+        elif kind == 2:                                      # matched to the codebook
+            seg = rng.choice(256, size=n, p=h / h.sum()).astype(np.uint8)
+        else:                                                # uniform over the used symbols
+            seg = rng.choice(syms, size=n).astype(np.uint8)
+        parts.append(seg)
+        total += n
+    data = np.concatenate(parts)
+    data = data[: data.size - data.size % 4]
+    ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
+    out, bits = gpu_encode(enc, torch_mod, data, cw, cl)
+    assert bits == ref_bits
+    assert np.array_equal(out[: ref_words.size], ref_words)
+    # the same shard in a global phase: shifted by start_bit % 32, first word's leading bits zero
+    sb = 64 * 7 + 13
+    out2, bits2 = gpu_encode(enc, torch_mod, data[: 9 * TILE + 8], cw, cl, start_bit=sb)
+    r2, rb2, _ = orc.encode(data[: 9 * TILE + 8].view(np.uint32), cw, cl)
+    assert bits2 == rb2
+    got_bits = np.unpackbits(out2[sb // 32: sb // 32 + rb2 // 32 + 2].byteswap().view(np.uint8))
+    want_bits = np.unpackbits(r2.byteswap().view(np.uint8))
+    assert np.array_equal(got_bits[sb % 32: sb % 32 + rb2], want_bits[:rb2]) and not got_bits[: sb % 32].any()
+
+
 @pytest.mark.parametrize("group", [4, 6, 8])
 @pytest.mark.parametrize("long_len", [17, 24, 31])
 def test_isolated_overlong_groups(enc, orc, torch_mod, monkeypatch, group, long_len):
