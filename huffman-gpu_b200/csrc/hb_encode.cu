@@ -497,11 +497,11 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
     const uint32_t ring_w = ring_window(wk);
 
     uint32_t sym = tail_symbol(first);
-    for (uint32_t k = first; k < K; k += 2u) {
+    for (uint32_t k = first; k < K; k += (uint32_t)kEncResolvers) {
         const uint32_t slot = slot_of(k);
         const unsigned long long tile = tile0 + (unsigned long long)k * gridDim.x;
         // this warp's next tile: its tail symbols have two tiles to land
-        const uint32_t sym_next = tail_symbol(k + 2u);
+        const uint32_t sym_next = tail_symbol(k + (uint32_t)kEncResolvers);
         long long t0 = prof.now();
         prof.count(kProfTiles);
 

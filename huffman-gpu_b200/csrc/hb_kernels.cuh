@@ -10,10 +10,14 @@
 namespace hb {
 
 // ---- geometry of the single-pass encoder ---------------------------------------------------------
-// One persistent CTA per SM: kEncWorkers worker warps + a publisher warp + two resolver warps.  A tile is the CTA's unit of
+// One persistent CTA per SM: kEncWorkers worker warps + a publisher warp + kEncResolvers resolver warps.  A tile is the CTA's unit of
 // work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
 constexpr int kEncWorkers = 16;
-constexpr int kEncThreads = (kEncWorkers + 3) * 32;
+#ifndef HB_RESOLVERS
+#define HB_RESOLVERS 2
+#endif
+constexpr int kEncResolvers = HB_RESOLVERS;                           // resolver warps: each takes every kEncResolvers-th tile
+constexpr int kEncThreads = (kEncWorkers + 1 + kEncResolvers) * 32;
 #ifndef HB_SYM_PER_THREAD
 #define HB_SYM_PER_THREAD 64
 #endif
