@@ -209,7 +209,7 @@ def run_reference_arm(args):
     run(cal.view(np.uint32), ccw, ccl, cbits)
     rate = cal.size / (time.perf_counter() - c0)                         # bytes/s of this box, one core
     want = int(args.cpu_budget_s * rate / max(1, args.steps + args.warmup))
-    sample = max(1 << 20, min(total, args.cpu_sample_mib << 20, want))
+    sample = max(16 << 20, min(total, args.cpu_sample_mib << 20, want))     # never a cache-resident sample
     sample -= sample % hb.capi.TILE_BYTES if sample >= hb.capi.TILE_BYTES else 0
     data = host_sample(hb, wl, sample)
     hist = np.bincount(data, minlength=256).astype(np.uint64)
