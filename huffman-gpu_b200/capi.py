@@ -8,7 +8,9 @@ LIB_PATH = os.environ.get("HB_LIB") or os.path.join(_HERE, "libhuffb200.so")    
 
 HB_OK = 0
 HB_ERR_ARG, HB_ERR_CAPACITY, HB_ERR_CODELEN, HB_ERR_CODEWORD = -1, -2, -3, -4
-HB_ERR_CUDA, HB_ERR_NOMEM, HB_ERR_STATE = -5, -6, -7
+HB_ERR_CUDA, HB_ERR_NOMEM, HB_ERR_STATE, HB_ERR_NCCL = -5, -6, -7, -8
+HB_UNIQUE_ID_BYTES = 128
+HB_MAX_RANKS = 64
 
 TILE_BYTES = None           # hb::kTileBytes, filled in by load()
 
@@ -16,6 +18,18 @@ u32p = C.POINTER(C.c_uint32)
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
 vp = C.c_void_p
+
+
+
+class ShardPlan(C.Structure):
+    """hb_shard_plan (include/huffman_b200.h)"""
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("max_len", C.c_int32), ("phase", C.c_uint32),
+                ("shard_bits", C.c_uint64), ("start_bit", C.c_uint64), ("total_bits", C.c_uint64),
+                ("first_word", C.c_uint64), ("local_words", C.c_uint64), ("local_offset_words", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
+planp = C.POINTER(ShardPlan)
 
 # name -> (restype, argtypes); mirrors include/huffman_b200.h declaration by declaration
 SIGNATURES = {
@@ -32,6 +46,18 @@ SIGNATURES = {
     "hb_vlc_encode_host": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, u32p, u32p, u64p, u64p]),
     "hb_host_alloc": (C.c_int, [C.POINTER(vp), C.c_uint64]),
     "hb_host_free": (None, [vp]),
+    "hb_comm_unique_id": (C.c_int, [u8p]),
+    "hb_comm_init": (C.c_int, [C.POINTER(vp), vp, C.c_int, C.c_int, u8p]),
+    "hb_comm_adopt": (C.c_int, [C.POINTER(vp), vp, vp, C.c_int, C.c_int]),
+    "hb_comm_free": (None, [vp]),
+    "hb_comm_last_nccl_error": (C.c_int, [vp]),
+    "hb_shard_plan_build": (C.c_int, [vp, vp, C.c_uint64, u32p, u32p, u64p, planp, vp]),
+    "hb_comm_plan_offsets": (C.c_int, [vp, u64p, u64p]),
+    "hb_shard_encode_async": (C.c_int, [vp, vp, C.c_uint64, u32p, u32p, vp, C.c_uint64, planp, vp]),
+    "hb_shard_encode_result": (C.c_int, [vp, u64p, vp]),
+    "hb_stitch_open": (C.c_int, [vp, C.c_uint64, C.c_int, C.POINTER(vp), vp]),
+    "hb_stitch_push": (C.c_int, [vp, vp, planp, vp]),
+    "hb_stitch_close": (C.c_int, [vp]),
     "hb_shard_offsets": (C.c_int, [u64p, C.c_int, u64p, u64p]),
     "hb_stitch_seam": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
     "hb_synth_fill": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32p,

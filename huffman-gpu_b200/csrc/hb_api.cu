@@ -17,51 +17,9 @@
 #include <new>
 
 #include "../../include/huffman_b200.h"
+#include "hb_ctx.h"
 #include "hb_kernels.cuh"
 
-struct hb_ctx {
-    int device = 0;
-    int sm_count = 0;
-    uint64_t max_words = 0;
-    uint64_t max_tiles = 0;
-
-    unsigned long long *d_tree[2] = {nullptr, nullptr};   // look-back Fenwick trees, used by alternate jobs
-    uint64_t tree_dirty[2] = {0, 0};          // entries a job left non-zero (cleared by the next job's kernel)
-    int tree_cur = 0;
-
-    uint32_t *d_table = nullptr;              // 512 words: packed[256] or wide uint2[256]
-    uint32_t *h_table = nullptr;              // pinned staging for the table upload
-    cudaEvent_t table_uploaded = nullptr;
-    uint32_t cw_cache[256];
-    uint32_t len_cache[256];
-    bool table_valid = false;
-    int forced = 0;                           // $HB_FORCE_GROUP the cached table was packed under
-    hb::EncVariant variant = {1, false, false};
-
-    hb::EncResult *h_result = nullptr;        // mapped pinned, kMaxChunks slots; the kernel writes them directly
-    uint64_t pending_start_bit = 0;
-    bool pending = false;
-    bool pending_empty = false;
-
-    unsigned long long *d_hist = nullptr;     // 256 bins
-    uint32_t *d_thr = nullptr;                // synth: thresholds
-    uint8_t *d_symmap = nullptr;
-
-    // host-buffer pipeline (hb_vlc_encode_host)
-    uint32_t *d_in_buf = nullptr;
-    uint64_t in_buf_words = 0;
-    uint32_t *d_out_buf = nullptr;
-    uint64_t out_buf_words = 0;
-    cudaStream_t s_main = nullptr;
-    cudaStream_t s_d2h = nullptr;
-    cudaStream_t s_h2d = nullptr;
-    cudaEvent_t ev_chunk[64] = {};            // one per launch of a chunked host job
-    cudaEvent_t ev_h2d[64] = {};              // ... and one per input copy
-
-    unsigned long long *d_prof = nullptr;     // $HB_PROFILE: kernel cycle counters, dumped by hb_free
-    uint64_t launches = 0;
-    int last_cuda = 0;
-};
 
 namespace {
 
@@ -168,36 +126,65 @@ int set_codebook(hb_ctx *ctx, const uint32_t cw[256], const uint32_t len[256], c
 
 uint64_t tiles_of(uint64_t n_words) { return (n_words + hb::kTileWords - 1) / hb::kTileWords; }
 
-// Launch the encode kernel over tiles [first_tile, end_tile) of a job.
-constexpr int kMaxChunks = 64;
+// where hist_kernel reports that it refused to run (mapped pinned: the device writes it, the host reads it)
+unsigned long long *hist_flag(hb_ctx *ctx) { return &ctx->h_result[kMaxChunks].overflow; }
 
+// The look-back trees after a failed or refused launch: nothing may be assumed about them any more.
+void reset_trees(hb_ctx *ctx)
+{
+    (void)cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) {
+        (void)cudaMemset(ctx->d_tree[i], 0, ctx->max_tiles * sizeof(unsigned long long));
+        ctx->tree_dirty[i] = 0;
+    }
+    (void)cudaDeviceSynchronize();
+    (void)cudaGetLastError();
+}
+
+// A context serialises its jobs: they share the device table, the result block and the two alternating trees.  A job
+// given another stream than the previous one is ordered behind it with an event (same stream: stream order).
+int order_after_previous_job(hb_ctx *ctx, cudaStream_t stream)
+{
+    if (ctx->have_last_stream && ctx->last_stream != stream)
+        HB_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->job_done, 0));
+    return HB_OK;
+}
+
+int job_launched(hb_ctx *ctx, cudaStream_t stream)
+{
+    HB_CUDA(ctx, cudaEventRecord(ctx->job_done, stream));
+    ctx->last_stream = stream;
+    ctx->have_last_stream = true;
+    return HB_OK;
+}
+
+// Launch the encode kernel over tiles [first_tile, end_tile) of a job.  A launch with first_tile == 0 starts a new job:
+// it takes the tree the previous job's kernel cleared and clears the previous job's tree in turn; that bookkeeping is
+// committed only once the launch has been accepted.
 int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t first_tile,
                  uint64_t end_tile, uint32_t *d_out, uint64_t cap_words, uint64_t start_bit,
                  cudaStream_t stream, int result_slot = 0)
 {
+    const bool new_job = first_tile == 0;
+    const int cur = new_job ? (ctx->tree_cur ^ 1) : ctx->tree_cur;
     hb::EncParams p;
     p.in = d_in;
     p.n_words = n_words;
     p.n_tiles = tiles_of(n_words);
+    if (p.n_tiles > hb::kMaxJobTiles) return HB_ERR_CAPACITY;      // the tree node's tile-count field (hb_encode.cu)
     p.first_tile = first_tile;
     p.end_tile = end_tile;
     p.out = d_out;
     p.out_cap_words = cap_words;
     p.start_bit = start_bit;
-    p.tree = ctx->d_tree[ctx->tree_cur];
-    p.tree_zero = ctx->d_tree[ctx->tree_cur ^ 1];
-    p.zero_count = 0;
-    if (first_tile == 0) {
-        // a new job: its kernel clears what the previous job left in the other tree
-        p.zero_count = ctx->tree_dirty[ctx->tree_cur ^ 1];
-        ctx->tree_dirty[ctx->tree_cur ^ 1] = 0;
-        ctx->tree_dirty[ctx->tree_cur] = p.n_tiles;
-    }
+    p.tree = ctx->d_tree[cur];
+    p.tree_zero = ctx->d_tree[cur ^ 1];
+    p.zero_count = new_job ? ctx->tree_dirty[cur ^ 1] : 0;
     p.table = ctx->d_table;
     p.result = ctx->h_result + result_slot;
     p.prof = ctx->d_prof;
     {
-        const char *pf = getenv("HB_L2_PREFETCH");
+        static const char *pf = getenv("HB_L2_PREFETCH");
         p.l2_prefetch = (pf && atoi(pf) == 0) ? 0u : 1u;    // measured: +1.4 % (1 GiB, H 2.2) .. +2.5 % (H 7.9); $HB_L2_PREFETCH=0 turns it off
     }
 
@@ -205,13 +192,20 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
     const uint64_t tiles = end_tile - first_tile;
     uint64_t grid = (uint64_t)ctx->sm_count;
     if (grid > tiles) grid = tiles;
-    HB_CUDA(ctx, hb::launch_encode(ctx->variant, p, (int)grid, stream));
+    const cudaError_t e = hb::launch_encode(ctx->variant, p, (int)grid, stream);
+    if (e != cudaSuccess) {
+        const int rc = cuda_fail(ctx, e);
+        reset_trees(ctx);                       // earlier launches of this job may have used the tree
+        return rc;
+    }
+    if (new_job) {
+        ctx->tree_cur = cur;
+        ctx->tree_dirty[cur ^ 1] = 0;           // being cleared by this kernel
+        ctx->tree_dirty[cur] = p.n_tiles;
+    }
     ctx->launches++;
     return HB_OK;
 }
-
-// Every job gets the tree the previous job's kernel cleared.
-void next_job(hb_ctx *ctx) { ctx->tree_cur ^= 1; }
 
 }  // namespace
 
@@ -244,38 +238,64 @@ int hb_init(hb_ctx **out, int device, uint64_t max_words)
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->max_words = max_words ? max_words : 1;
+    if (tiles_of(ctx->max_words) > hb::kMaxJobTiles) {          // 64 GiB of input per job (hb_encode.cu, tree node layout)
+        delete ctx;
+        return HB_ERR_CAPACITY;
+    }
     ctx->max_tiles = tiles_of(ctx->max_words) + 1;
 
-    bool ok = true;
-    for (int i = 0; i < 2; i++) {
-        ok = ok && cudaMalloc(&ctx->d_tree[i], ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMemset(ctx->d_tree[i], 0, ctx->max_tiles * sizeof(unsigned long long)) == cudaSuccess;
+    // the first failing call decides the status: allocation failures are HB_ERR_NOMEM, anything else HB_ERR_CUDA
+    cudaError_t first = cudaSuccess;
+    auto tryc = [&](cudaError_t r) {
+        if (first == cudaSuccess && r != cudaSuccess) first = r;
+        return first == cudaSuccess;
+    };
+    for (int i = 0; i < 2; i++)
+        if (tryc(cudaMalloc(&ctx->d_tree[i], ctx->max_tiles * sizeof(unsigned long long))))
+            tryc(cudaMemset(ctx->d_tree[i], 0, ctx->max_tiles * sizeof(unsigned long long)));
+    tryc(cudaMalloc(&ctx->d_table, 512 * sizeof(uint32_t)));
+    tryc(cudaMallocHost(&ctx->h_table, 512 * sizeof(uint32_t)));
+    tryc(cudaHostAlloc(&ctx->h_result, (kMaxChunks + 1) * sizeof(hb::EncResult), cudaHostAllocMapped));
+    tryc(cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)));
+    tryc(cudaMalloc(&ctx->d_thr, 256 * sizeof(uint32_t)));
+    tryc(cudaMalloc(&ctx->d_symmap, 256));
+    tryc(cudaEventCreateWithFlags(&ctx->table_uploaded, cudaEventDisableTiming));
+    tryc(cudaEventCreateWithFlags(&ctx->job_done, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxChunks; i++) {
+        tryc(cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming));
+        tryc(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
     }
-    ok = ok && cudaMalloc(&ctx->d_table, 512 * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMallocHost(&ctx->h_table, 512 * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaHostAlloc(&ctx->h_result, kMaxChunks * sizeof(hb::EncResult), cudaHostAllocMapped) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_hist, 256 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_thr, 256 * sizeof(uint32_t)) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_symmap, 256) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&ctx->table_uploaded, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < kMaxChunks; i++)
-        ok = ok && cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) == cudaSuccess;
+    tryc(cudaStreamCreateWithFlags(&ctx->s_main, cudaStreamNonBlocking));
+    tryc(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    tryc(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     if (getenv("HB_PROFILE")) {
         // 32 global counters, then per worker index: cycles spent waiting for records, and the worker's total
-        ok = ok && cudaMalloc(&ctx->d_prof, (32 + 512 + 1280 + 960) * sizeof(unsigned long long)) == cudaSuccess;
-        ok = ok && cudaMemset(ctx->d_prof, 0, (32 + 512 + 1280 + 960) * sizeof(unsigned long long)) == cudaSuccess;
+        if (tryc(cudaMalloc(&ctx->d_prof, (32 + 512 + 1280 + 960) * sizeof(unsigned long long))))
+            tryc(cudaMemset(ctx->d_prof, 0, (32 + 512 + 1280 + 960) * sizeof(unsigned long long)));
     }
-    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
-    if (!ok) {
-        ctx->last_cuda = (int)cudaGetLastError();
+    tryc(cudaDeviceSynchronize());
+    if (first == cudaSuccess) {
+        // The histogram kernel refuses to run when the shared window is not laid out as it assumes, and says so in
+        // the result block (never in the data).  That is a property of driver + kernel image: probe it once, here, so
+        // that the asynchronous hb_histogram_device can never hand a refused histogram to the codebook builder.
+        memset(ctx->h_result, 0, (kMaxChunks + 1) * sizeof(hb::EncResult));
+        tryc(cudaMemset(ctx->d_hist, 0, 256 * sizeof(unsigned long long)));
+        tryc(cudaMemset(ctx->d_table, 0, 512 * sizeof(uint32_t)));
+        tryc(hb::launch_histogram(ctx->d_table, 16, ctx->d_hist, ctx->sm_count, hist_flag(ctx), nullptr));
+        tryc(cudaDeviceSynchronize());
+        if (first == cudaSuccess && ctx->h_result[kMaxChunks].overflow) {
+            fprintf(stderr, "hb_init: hist_kernel refused its shared-memory layout on this driver\n");
+            hb_free(ctx);
+            return HB_ERR_STATE;
+        }
+    }
+    if (first != cudaSuccess) {
+        const int rc = first == cudaErrorMemoryAllocation ? HB_ERR_NOMEM : HB_ERR_CUDA;
+        fprintf(stderr, "hb_init: CUDA error %d (%s)\n", (int)first, cudaGetErrorString(first));
+        (void)cudaGetLastError();
         hb_free(ctx);
-        return HB_ERR_NOMEM;
+        return rc;
     }
-    memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
     *out = ctx;
     return HB_OK;
 }
@@ -364,6 +384,7 @@ void hb_free(hb_ctx *ctx)
     cudaFree(ctx->d_in_buf);
     cudaFree(ctx->d_out_buf);
     if (ctx->table_uploaded) cudaEventDestroy(ctx->table_uploaded);
+    if (ctx->job_done) cudaEventDestroy(ctx->job_done);
     for (int i = 0; i < kMaxChunks; i++) {
         if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
         if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
@@ -380,7 +401,8 @@ int hb_histogram_device(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uin
 {
     if (!ctx || !d_hist || (!d_in && n_words) || ((uintptr_t)d_in & 3u)) return HB_ERR_ARG;
     DeviceGuard g(ctx->device);
-    HB_CUDA(ctx, hb::launch_histogram(d_in, n_words, (unsigned long long *)d_hist, ctx->sm_count,
+    if (*(volatile unsigned long long *)hist_flag(ctx)) return HB_ERR_STATE;     // refused before (see hb_init)
+    HB_CUDA(ctx, hb::launch_histogram(d_in, n_words, (unsigned long long *)d_hist, ctx->sm_count, hist_flag(ctx),
                                       (cudaStream_t)stream));
     if (n_words) ctx->launches++;
     return HB_OK;
@@ -397,7 +419,7 @@ int hb_histogram(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t h
     HB_CUDA(ctx, cudaMemcpyAsync(hist, ctx->d_hist, 256 * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, st));
     HB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (hist[0] > n_words * 4ULL) return HB_ERR_STATE;       // the kernel refused its shared-memory layout (hb_misc.cu)
+    if (*(volatile unsigned long long *)hist_flag(ctx)) return HB_ERR_STATE;     // the kernel refused its shared-memory layout
     return HB_OK;
 }
 
@@ -411,8 +433,11 @@ int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const u
     if (start_bit >> 47) return HB_ERR_ARG;
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = set_codebook(ctx, codewords, codewordlens, st);
+    // a job on another stream than the previous one waits for it: the table upload below must not overtake a kernel
+    // that still reads the old table
+    int rc = order_after_previous_job(ctx, st);
     if (rc != HB_OK) return rc;
+    if ((rc = set_codebook(ctx, codewords, codewordlens, st)) != HB_OK) return rc;
 
     // Several encodes may be queued on the same stream: the kernel only ever SETS result->overflow and
     // the last launch's last tile writes result->bits_end; the host touches the block in
@@ -427,9 +452,9 @@ int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const u
         ctx->pending_start_bit = start_bit;
         return HB_OK;
     }
-    next_job(ctx);
     rc = launch_tiles(ctx, d_in, n_words, 0, tiles_of(n_words), d_out, out_capacity_words, start_bit, st);
     if (rc != HB_OK) return rc;
+    if ((rc = job_launched(ctx, st)) != HB_OK) return rc;
     ctx->pending = true;
     ctx->pending_empty = false;
     ctx->pending_start_bit = start_bit;
@@ -447,7 +472,10 @@ int hb_encode_result(hb_ctx *ctx, uint64_t *total_bits, void *stream)
     ctx->h_result->overflow = 0;
     if (total_bits)
         *total_bits = ctx->pending_empty ? 0 : ctx->h_result->bits_end - ctx->pending_start_bit;
-    if (overflow == 2ULL) return HB_ERR_STATE;      // the kernel refused its shared-memory layout
+    if (overflow == 2ULL) {                          // the kernel refused its shared-memory layout: it cleared nothing
+        reset_trees(ctx);
+        return HB_ERR_STATE;
+    }
     return overflow ? HB_ERR_CAPACITY : HB_OK;
 }
 
@@ -506,6 +534,7 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
         HB_CUDA(ctx, cudaDeviceSynchronize());
         ctx->pending = false;
     }
+    if ((rc = order_after_previous_job(ctx, st)) != HB_OK) return rc;
     if ((rc = set_codebook(ctx, codewords, codewordlens, st)) != HB_OK) return rc;
     memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
 
@@ -513,7 +542,6 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
     if (n_words == 0) {
         h_out[0] = 0;                          // cpuencode.cpp:17
     } else {
-        next_job(ctx);
         // Chunked, three streams: the H2D copies run back to back on their own stream, the encode of chunk k (which
         // waits for copy k only) overlaps copy k+1, and the D2H copy of the words chunk k completed overlaps both
         // (PCIe is full duplex).  Small chunks keep the fill (first copy) and the drain (last encode + last D2H) short.
@@ -526,40 +554,71 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
         if (chunk_tiles < 1) chunk_tiles = 1;
         if ((total_tiles + chunk_tiles - 1) / chunk_tiles > (uint64_t)kMaxChunks)    // ... at most kMaxChunks of them
             chunk_tiles = (total_tiles + kMaxChunks - 1) / kMaxChunks;
+        // Every exit after the first launch goes through `fail`: launches may still be queued on s_main and copies into
+        // the caller's h_out in flight on s_d2h; nothing may be left running, dirty or half-ordered behind our back.
+        bool launched = false, kernel_state_lost = false;
+        auto fail = [&](int status) {
+            if (launched) {
+                (void)cudaStreamSynchronize(ctx->s_h2d);
+                (void)cudaStreamSynchronize(st);
+                (void)cudaStreamSynchronize(ctx->s_d2h);
+                (void)cudaGetLastError();
+                (void)job_launched(ctx, st);
+            }
+            memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
+            if (kernel_state_lost) reset_trees(ctx);
+            return status;
+        };
+#define HB_TRY(call)                                             \
+        do {                                                     \
+            cudaError_t e__ = (call);                            \
+            if (e__ != cudaSuccess) return fail(cuda_fail(ctx, e__)); \
+        } while (0)
         int n_chunks = 0;
         for (uint64_t t0 = 0; t0 < total_tiles; t0 += chunk_tiles, n_chunks++) {
             const uint64_t t1 = (t0 + chunk_tiles < total_tiles) ? t0 + chunk_tiles : total_tiles;
             const uint64_t w0 = t0 * hb::kTileWords;
             const uint64_t w1 = (t1 * hb::kTileWords < n_words) ? t1 * hb::kTileWords : n_words;
-            HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_in_buf + w0, h_in + w0, (w1 - w0) * sizeof(uint32_t),
-                                         cudaMemcpyHostToDevice, ctx->s_h2d));
-            HB_CUDA(ctx, cudaEventRecord(ctx->ev_h2d[n_chunks], ctx->s_h2d));
-            HB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_h2d[n_chunks], 0));
+            HB_TRY(cudaMemcpyAsync(ctx->d_in_buf + w0, h_in + w0, (w1 - w0) * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, ctx->s_h2d));
+            HB_TRY(cudaEventRecord(ctx->ev_h2d[n_chunks], ctx->s_h2d));
+            HB_TRY(cudaStreamWaitEvent(st, ctx->ev_h2d[n_chunks], 0));
             rc = launch_tiles(ctx, ctx->d_in_buf, n_words, t0, t1, ctx->d_out_buf, dev_out_words, 0, st, n_chunks);
-            if (rc != HB_OK) return rc;
-            HB_CUDA(ctx, cudaEventRecord(ctx->ev_chunk[n_chunks], st));
+            if (rc != HB_OK) {
+                // A later launch of a job that never happens leaves the earlier ones polling tree nodes nobody will
+                // complete: launch_tiles has already synchronised the device and reset the trees in that case.
+                return fail(rc);
+            }
+            launched = true;
+            HB_TRY(cudaEventRecord(ctx->ev_chunk[n_chunks], st));
         }
         // as each launch retires, every output word below its end bit is final: send it home
         uint64_t done_words = 0;
         for (int c = 0; c < n_chunks; c++) {
-            HB_CUDA(ctx, cudaEventSynchronize(ctx->ev_chunk[c]));
-            if (ctx->h_result[c].overflow == 2ULL) return HB_ERR_STATE;
-            if (ctx->h_result[c].overflow) return HB_ERR_CAPACITY;
+            HB_TRY(cudaEventSynchronize(ctx->ev_chunk[c]));
+            if (ctx->h_result[c].overflow == 2ULL) {
+                kernel_state_lost = true;
+                return fail(HB_ERR_STATE);
+            }
+            if (ctx->h_result[c].overflow) return fail(HB_ERR_CAPACITY);
             bits = ctx->h_result[c].bits_end;
             // the last launch also owns the final partial word and the reference's courtesy zero word
             uint64_t upto = (c + 1 == n_chunks) ? bits / 32 + 1 : bits / 32;
             if (c + 1 == n_chunks) {
                 if (upto > out_capacity_words) upto = out_capacity_words;
-                if (upto < (bits + 31) / 32) return HB_ERR_CAPACITY;
+                if (upto < (bits + 31) / 32) return fail(HB_ERR_CAPACITY);
             }
             if (upto > done_words) {
-                HB_CUDA(ctx, cudaMemcpyAsync(h_out + done_words, ctx->d_out_buf + done_words,
-                                             (upto - done_words) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                             ctx->s_d2h));
+                HB_TRY(cudaMemcpyAsync(h_out + done_words, ctx->d_out_buf + done_words,
+                                       (upto - done_words) * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                       ctx->s_d2h));
                 done_words = upto;
             }
         }
-        HB_CUDA(ctx, cudaStreamSynchronize(ctx->s_d2h));
+        HB_TRY(cudaStreamSynchronize(ctx->s_d2h));
+#undef HB_TRY
+        if ((rc = job_launched(ctx, st)) != HB_OK) return rc;
+        memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
     }
     if (total_bits) *total_bits = bits;
     if (out_bytes) *out_bytes = (bits + 7) / 8;
@@ -661,12 +720,13 @@ const char *hb_strerror(int status)
     case HB_ERR_CUDA: return "CUDA error (see hb_last_cuda_error)";
     case HB_ERR_NOMEM: return "out of memory";
     case HB_ERR_STATE: return "call sequence error";
+    case HB_ERR_NCCL: return "NCCL unavailable or an NCCL call failed (see hb_comm_last_nccl_error)";
     default: return "unknown status";
     }
 }
 
 int hb_last_cuda_error(const hb_ctx *ctx) { return ctx ? ctx->last_cuda : 0; }
 
-const char *hb_version(void) { return "huffman-b200 0.1 (sm_100a)"; }
+const char *hb_version(void) { return "huffman-b200 0.2 (sm_100a)"; }
 
 }  // extern "C"

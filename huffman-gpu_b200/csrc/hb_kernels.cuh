@@ -25,6 +25,9 @@ constexpr int kSymPerThread = HB_SYM_PER_THREAD;                                
 constexpr int kChunkBytes = 32 * kSymPerThread;                       // one warp: 2 KiB
 constexpr int kTileBytes = kEncWorkers * kChunkBytes;                 // 32 KiB
 constexpr int kTileWords = kTileBytes / 4;
+// A look-back tree node counts tiles in 22 bits and sums bits in 42 (hb_encode.cu): a job has at most 2^21 tiles
+// (64 GiB of input; a node then counts at most 2^20 tiles and sums at most 64 GiB * 31 bits < 2^42).
+constexpr unsigned long long kMaxJobTiles = 1ULL << 21;
 
 // Written by the kernel into mapped pinned host memory (zero-copy), read by the host after sync.
 struct EncResult {
@@ -72,7 +75,8 @@ cudaError_t launch_encode(const EncVariant &v, const EncParams &p, int grid, cud
 
 cudaError_t histogram_configure();                     // opt-in smem attribute, once per device context
 cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
-                             unsigned long long *d_hist, int sm_count, cudaStream_t stream);
+                             unsigned long long *d_hist, int sm_count, unsigned long long *refused,
+                             cudaStream_t stream);
 cudaError_t launch_or_words(uint32_t *d_dst, const uint32_t *d_src, unsigned long long n_words,
                             cudaStream_t stream);
 cudaError_t launch_synth(uint8_t *d_out, unsigned long long first, unsigned long long n,

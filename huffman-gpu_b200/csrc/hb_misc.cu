@@ -39,14 +39,16 @@ __device__ __forceinline__ void count_word(uint32_t col, uint32_t w)
 
 __global__ void __launch_bounds__(kHistThreads, 1) hist_kernel(const uint32_t *__restrict__ in,
                                                                unsigned long long n_words,
-                                                               unsigned long long *__restrict__ hist)
+                                                               unsigned long long *__restrict__ hist,
+                                                               unsigned long long *refused)
 {
     extern __shared__ __align__(1024) uint32_t hist_smem[];
     uint32_t *bins = hist_smem + (kHistBinsWindow - kHistReserved) / 4;
     const uint32_t tid = threadIdx.x;
     if ((uint32_t)__cvta_generic_to_shared(bins) != kHistBinsWindow) {
-        // the shared window is not laid out as assumed: refuse loudly (the host checks this bin) instead of miscounting
-        if (tid == 0 && blockIdx.x == 0) atomicAdd(&hist[0], ~0ULL >> 1);
+        // the shared window is not laid out as assumed: refuse loudly instead of miscounting -- through the context's
+        // result block (mapped host memory), never through the data
+        if (tid == 0 && blockIdx.x == 0) *refused = 1ULL;
         return;
     }
     for (uint32_t i = tid; i < 256u * 64u; i += kHistThreads) bins[i] = 0u;
@@ -162,7 +164,8 @@ cudaError_t histogram_configure()
 }
 
 cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
-                             unsigned long long *d_hist, int sm_count, cudaStream_t stream)
+                             unsigned long long *d_hist, int sm_count, unsigned long long *refused,
+                             cudaStream_t stream)
 {
     if (n_words == 0) return cudaSuccess;
     // one CTA of 1024 threads per SM (its 64 KiB of bins sit on a 64 KiB boundary of the shared window),
@@ -172,7 +175,7 @@ cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
     if (want < 1) want = 1;
     const unsigned long long cap = (unsigned long long)sm_count;
     const int grid = (int)(want < cap ? want : cap);
-    hist_kernel<<<grid, kHistThreads, kHistSmemBytes, stream>>>(d_in, n_words, d_hist);
+    hist_kernel<<<grid, kHistThreads, kHistSmemBytes, stream>>>(d_in, n_words, d_hist, refused);
     return cudaGetLastError();
 }
 

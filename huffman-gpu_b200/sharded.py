@@ -11,14 +11,21 @@ Rank r then encodes with start_bit = off_r % 32 so that its words are already in
 The optional stitch gathers the shards on rank 0 (NCCL send/recv, NVLink P2P): shard r's words land
 at global word off_r // 32; the seam word shared with shard r-1 is OR-ed (hb_stitch_seam).
 
-The plumbing takes any torch.distributed backend (NCCL on GPUs; gloo on CPU for the host-logic tests)
-and an `encode_fn`, which on a GPU box is Encoder.encode.
+Two implementations of the same plan:
+  * ShardComm -- the C ABI (hb_comm_* / hb_shard_* / hb_stitch_*, csrc/hb_comm.cu): NCCL called from C on the
+    caller's stream, the stitch as concurrent peer stores over NVLink into an IPC-mapped buffer on the root GPU.
+    This is the product path on GPUs (bench.py, the -m gpu tests).
+  * make_plan / stitch_on_rank0 -- the same arithmetic over any torch.distributed backend; used with gloo on CPU
+    to test the host logic with world sizes > 1, and as a cross-check of ShardComm on GPUs.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from .encoder import bits_from_hist, build_codebook, shard_offsets
+from . import capi
+from .encoder import _check, bits_from_hist, build_codebook, lib, shard_offsets
 
 
 def shard_bounds(n_words, world, tile_words=None):
@@ -118,3 +125,109 @@ def stitch_on_rank0(plan, local_words, group=None, or_fn=None):
         else:
             out[w0:w0 + n].copy_(part[:n])
     return out
+
+
+# ---- the C-ABI path ---------------------------------------------------------------------------------------------
+class ShardComm:
+    """hb_comm over an Encoder (one per rank).  The 128-byte NCCL unique id is created on rank 0 and handed to the
+    other ranks through `bcast(bytes_or_None) -> bytes`, any channel the caller has (default: torch.distributed)."""
+
+    def __init__(self, enc, rank, world, bcast=None):
+        self.enc, self.rank, self.world = enc, int(rank), int(world)
+        uid = (C.c_uint8 * capi.HB_UNIQUE_ID_BYTES)()
+        if self.rank == 0:
+            _check(lib().hb_comm_unique_id(uid), "hb_comm_unique_id")
+        if bcast is None:
+            t = torch.tensor(list(uid), dtype=torch.uint8)
+            dev = torch.device("cuda", enc.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = t.to(dev)
+            dist.broadcast(t, src=0)
+            payload = bytes(t.cpu().tolist())
+        else:
+            payload = bcast(bytes(uid) if self.rank == 0 else None)
+        uid = (C.c_uint8 * capi.HB_UNIQUE_ID_BYTES).from_buffer_copy(payload)
+        self._comm = capi.vp()
+        _check(lib().hb_comm_init(C.byref(self._comm), enc._ctx, self.rank, self.world, uid), "hb_comm_init", enc._ctx)
+        self.plan = None
+        self.stitched_ptr = None
+
+    def close(self):
+        if self._comm:
+            lib().hb_comm_free(self._comm)
+            self._comm = capi.vp()
+
+    def _ck(self, status, where):
+        if status == capi.HB_ERR_NCCL:
+            raise capi.HBError(lib(), status, "%s (ncclResult %d)" % (where, lib().hb_comm_last_nccl_error(self._comm)))
+        return _check(status, where, self.enc._ctx)
+
+    def plan_build(self, d_in):
+        """collective: histogram -> all-reduce -> codebook -> all-gather.  -> (codewords, codewordlens, plan, hist_global)"""
+        ptr, n_words = self.enc._words(d_in)
+        cw = np.zeros(256, dtype=np.uint32)
+        cl = np.zeros(256, dtype=np.uint32)
+        hist = np.zeros(256, dtype=np.uint64)
+        plan = capi.ShardPlan()
+        self._ck(lib().hb_shard_plan_build(self._comm, ptr, n_words, cw.ctypes.data_as(capi.u32p),
+                                           cl.ctypes.data_as(capi.u32p), hist.ctypes.data_as(capi.u64p),
+                                           C.byref(plan), self.enc._stream()), "hb_shard_plan_build")
+        self.plan = plan
+        return cw, cl, plan, hist
+
+    def offsets(self):
+        starts = np.zeros(self.world, dtype=np.uint64)
+        bits = np.zeros(self.world, dtype=np.uint64)
+        self._ck(lib().hb_comm_plan_offsets(self._comm, starts.ctypes.data_as(capi.u64p),
+                                            bits.ctypes.data_as(capi.u64p)), "hb_comm_plan_offsets")
+        return starts, bits
+
+    def local_buffer(self, plan=None):
+        """a device buffer for this rank's words (int32), sized as hb_shard_plan asks"""
+        plan = plan or self.plan
+        return torch.empty(int(plan.local_offset_words + plan.local_words + 1), dtype=torch.int32,
+                           device=torch.device("cuda", self.enc.device))
+
+    def encode_async(self, d_in, cw, cl, d_local, plan=None):
+        plan = plan or self.plan
+        ptr, n_words = self.enc._words(d_in)
+        optr, cap = self.enc._words(d_local)
+        cw = np.ascontiguousarray(cw, dtype=np.uint32)
+        cl = np.ascontiguousarray(cl, dtype=np.uint32)
+        self._ck(lib().hb_shard_encode_async(self._comm, ptr, n_words, cw.ctypes.data_as(capi.u32p),
+                                             cl.ctypes.data_as(capi.u32p), optr, cap, C.byref(plan),
+                                             self.enc._stream()), "hb_shard_encode_async")
+
+    def encode_result(self):
+        bits = C.c_uint64(0)
+        self._ck(lib().hb_shard_encode_result(self._comm, C.byref(bits), self.enc._stream()), "hb_shard_encode_result")
+        return int(bits.value)
+
+    def local_words_view(self, d_local, plan=None):
+        plan = plan or self.plan
+        o = int(plan.local_offset_words)
+        return d_local[o:o + int(plan.local_words) + 1]
+
+    def stitch_open(self, capacity_words, root=0):
+        p = capi.vp()
+        self._ck(lib().hb_stitch_open(self._comm, int(capacity_words), int(root), C.byref(p), self.enc._stream()),
+                 "hb_stitch_open")
+        self.stitched_ptr, self.stitch_root, self.stitch_cap = p.value, int(root), int(capacity_words)
+        return p.value
+
+    def stitch_push(self, d_local, plan=None):
+        plan = plan or self.plan
+        self._ck(lib().hb_stitch_push(self._comm, d_local.data_ptr(), C.byref(plan), self.enc._stream()),
+                 "hb_stitch_push")
+
+    def stitched_view(self, n_words):
+        """root only: the first n_words of the stitched stream as an int32 torch tensor (a view, no copy)"""
+        assert self.rank == self.stitch_root and n_words <= self.stitch_cap
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (int(n_words),), "typestr": "<i4",
+                                        "data": (int(self.stitched_ptr), False), "version": 2}
+        return torch.as_tensor(_Raw(), device=torch.device("cuda", self.enc.device))
+
+    def stitch_close(self):
+        self._ck(lib().hb_stitch_close(self._comm), "hb_stitch_close")
+        self.stitched_ptr = None

@@ -2,6 +2,7 @@
 generated from the unmodified cpuencode.cpp / huffTree.h (oracle/make_golden.py), and -- when the
 prebuilt oracle/_ref/libref.so is present -- the reference itself on fresh random inputs."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -149,3 +150,32 @@ def test_synth_c4_exact_counts(hb, orc):
     g = [c for c in load_golden("codebooks.json") if c.get("name") == "c4_fibonacci"][0]
     assert g["rc"] == 31 and sorted(set(g["codewordlens"])) == list(range(0, 32))
     assert w.nbits == 31 and w.thr.size == 32
+
+
+def test_golden_stream_c2_restatement_at_full_size(orc):
+    """tests/golden/streams.json (made by oracle/make_golden_streams.py from the UNMODIFIED cpu_vlc_encode): the
+    restatement reproduces the C2 entry -- generator, histogram, tree builder, encoder, and the numpy side of the
+    parallel checksums the GPU tests and bench.py use at full size."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mods = {}
+    for name in ("workloads", "streamsum"):
+        spec = importlib.util.spec_from_file_location("hb_" + name, os.path.join(root, "huffman-gpu_b200", name + ".py"))
+        mods[name] = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mods[name])
+    g = load_golden("streams.json")
+    assert set(g) >= {"c2", "t1g", "c3", "c4", "c5"}
+    for e in g.values():
+        assert e["encoder"].startswith("cpu_vlc_encode (cpuencode.cpp:12-46, unmodified")
+        assert sum(e["hist"]) == e["n_bytes"]
+        assert sum(h * l for h, l in zip(e["hist"], e["codewordlens"])) == e["total_bits"]
+    wl = mods["workloads"].get("c2")
+    data = orc.synth_fill(0, wl.n_bytes, wl.seed, wl.mode, wl.nbits, wl.thr)
+    hist = orc.histogram(data)
+    assert hist.tolist() == g["c2"]["hist"]
+    rc, cw, cl = orc.build_codebook(hist)
+    assert cl.tolist() == g["c2"]["codewordlens"] and cw.tolist() == g["c2"]["codewords"]
+    out, bits, _ = orc.encode(data.view(np.uint32), cw, cl, total_bits_hint=g["c2"]["total_bits"])
+    assert bits == g["c2"]["total_bits"] and out.size == g["c2"]["n_words"]
+    assert "0x%016x" % orc.word_fnv(out) == g["c2"]["word_fnv"]
+    assert ["0x%016x" % s for s in mods["streamsum"].stream_sums(out)] == g["c2"]["sums"]

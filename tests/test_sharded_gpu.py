@@ -3,7 +3,11 @@
 
   * one GPU: the shards are encoded one after the other on the same device (same kernels, same phases,
     same stitch), which is what a rank does;
-  * two or more GPUs: torch.distributed over NCCL, one process per GPU (spawned here)."""
+  * two or more GPUs, torch path: torch.distributed over NCCL, one process per GPU (spawned here);
+  * two or more GPUs, C-ABI path (hb_comm_* / hb_shard_* / hb_stitch_*): NCCL called from C, the unique id handed
+    over through plain multiprocessing queues (no torch.distributed at all), the stitch as peer stores over NVLink
+    into the root's IPC-mapped buffer.  Small cases are compared word by word with the CPU oracle; the full C4
+    (2 GiB on 2 GPUs) and C5 (8 GiB on 2/4/8 GPUs) streams with the golden checksums of the unmodified reference."""
 import os
 import sys
 
@@ -121,3 +125,119 @@ def test_shards_nccl_two_gpus(native_built):
         p.join(300)
         assert p.exitcode == 0
     assert ret.get(timeout=5) == "ok"
+
+
+# ---- the C-ABI multi-GPU path -----------------------------------------------------------------------------------
+def _comm_worker(rank, world, queues, name, n_bytes, ret):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import json
+    import torch
+    import pyoracle
+    import huffman_gpu_b200 as hb
+    from huffman_gpu_b200 import sharded
+    from huffman_gpu_b200.streamsum import stream_sums
+    try:
+        torch.cuda.set_device(rank)
+        wl = hb.workloads.get(name) if n_bytes is None else hb.workloads.get(name, n_bytes=n_bytes)
+        n_words = wl.n_bytes // 4
+        lo, hi = sharded.shard_bounds(n_words, world)[rank]
+        enc = hb.Encoder(device=rank, max_bytes=max(4, (hi - lo) * 4))
+
+        def bcast(payload):                                  # the caller's own channel for the 128-byte NCCL id
+            if rank == 0:
+                for q in queues[1:]:
+                    q.put(payload)
+                return payload
+            return queues[rank].get(timeout=120)
+        comm = sharded.ShardComm(enc, rank, world, bcast=bcast)
+        d_in = torch.empty((hi - lo) * 4, dtype=torch.uint8, device="cuda")
+        if hi > lo:
+            enc.synth_fill(d_in, wl, first=lo * 4)           # bytes [lo*4, hi*4) of ONE logical stream
+        cw, cl, plan, hist = comm.plan_build(d_in)            # hist kernel -> ncclAllReduce -> codebook -> ncclAllGather
+        d_local = comm.local_buffer()
+        d_local.fill_(0x5A5A5A5A)
+        comm.encode_async(d_in, cw, cl, d_local)
+        assert comm.encode_result() == plan.shard_bits
+        cap = plan.total_bits // 32 + 2
+        comm.stitch_open(cap, root=0)
+        comm.stitch_push(d_local)
+        torch.cuda.synchronize()
+        if rank == 0:
+            n = plan.total_bits // 32 + 1
+            got_t = comm.stitched_view(n)
+            if wl.n_bytes <= (64 << 20):
+                orc = pyoracle.Oracle()
+                data = orc.synth_fill(0, wl.n_bytes, wl.seed, wl.mode, wl.nbits, wl.thr, wl.symmap)
+                assert np.array_equal(hist, orc.histogram(data))
+                ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
+                assert ref_bits == plan.total_bits
+                got = got_t.cpu().numpy().view(np.uint32)
+                bad = np.nonzero(got != ref_words[:n])[0]
+                assert bad.size == 0, "first mismatch at word %d of %d" % (bad[0], n)
+            else:
+                g = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))[name]
+                assert plan.total_bits == g["total_bits"]
+                assert np.array_equal(hist, np.array(g["hist"], dtype=np.uint64))
+                assert np.array_equal(cl, np.array(g["codewordlens"], dtype=np.uint32))
+                sums = stream_sums(got_t, n)
+                assert ["0x%016x" % x for x in sums] == g["sums"], "stitched stream differs from cpu_vlc_encode's"
+            ret.put("ok")
+        comm.stitch_close()
+        comm.close()
+        enc.close()
+    except BaseException as exc:                              # a dead rank must not leave the others in a collective
+        ret.put("rank %d: %r" % (rank, exc))
+        raise
+
+
+def _run_comm(world, name, n_bytes, timeout=600):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    queues = [ctx.Queue() for _ in range(world)]
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, queues, name, n_bytes, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    msg = ret.get(timeout=timeout)
+    for p in procs:
+        p.join(60)
+        if p.is_alive():
+            p.kill()
+    assert msg == "ok", msg
+    assert all(p.exitcode == 0 for p in procs)
+
+
+@pytest.mark.parametrize("name,n_bytes", [("c5", 6 << 20), ("c5", 3 * 32768 + 4096), ("c5", 4096), ("c2", 8 << 20),
+                                          ("c3", (5 << 20) + 32768 + 8)])
+def test_comm_two_gpus_small(native_built, name, n_bytes):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_comm(2, name, n_bytes)
+
+
+def test_comm_c4_on_two_gpus_full(native_built):
+    """BASELINE config 4: 2 GiB Fibonacci-skewed (code lengths 1..31) on 2 B200, stitched stream == cpu_vlc_encode's"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_comm(2, "c4", None)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_comm_c5_full(native_built, world):
+    """BASELINE config 5: 8 GiB at H~4 sharded over 2/4/8 B200, stitched stream == cpu_vlc_encode's"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _run_comm(world, "c5", None)
+
+
+@pytest.mark.parametrize("world,n_bytes", [(4, 2_000_000), (8, 8 << 20), (3, 32768 + 4096)])
+def test_comm_many_gpus_small(native_built, world, n_bytes):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    _run_comm(world, "c5", n_bytes)
