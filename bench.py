@@ -457,7 +457,17 @@ def main():
     d_in, lo, hi = B.load_shard(enc, wl)
 
     # ---- histogram -> all-reduce -> codebook -> all-gather (C ABI, NCCL from C) ----------------------------------
-    comm = sharded.ShardComm(enc, rank, world) if world > 1 else None
+    comm = None
+    if world > 1:
+        # NCCL prints its version banner to stdout when $NCCL_DEBUG asks for it: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            comm = sharded.ShardComm(enc, rank, world)
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     if comm is not None:
         cw, cl, plan, hist_global = comm.plan_build(d_in)
         max_len, my_bits, start_bit, total_bits = plan.max_len, int(plan.shard_bits), int(plan.phase), int(plan.total_bits)
