@@ -624,25 +624,40 @@ template <bool SWZ>
 __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t ring_s, uint32_t i0, uint32_t cnt,
                                          uint32_t first_before, uint32_t sh, uint32_t lane)
 {
-    // two words per lane per trip, every trip independent of the others (loads first, then stores).  A row of 32
-    // staged words further on is 32 (+ 1 pad) words further on in the ring, whatever the alignment of i0.
+    // Row r = the 32 output words 32 r + lane.  A row of 32 staged words further on is 32 (+ 1 pad) words further on
+    // in the ring, whatever the alignment of i0, so every load below is base + compile-time offset.  Row 0 is peeled
+    // (its lane 0 takes the carry-in instead of a staged predecessor); then four full rows per trip, loads first;
+    // then up to three more full rows and the ragged last row under one compare each.  (The former loop, two rows per
+    // trip with the carry-in select and the bounds inside: 23 issue slots per 64 words, 100 per chunk at H 2.2.)
     constexpr uint32_t kRow = SWZ ? 132u : 128u;
     const uint32_t idx = i0 + lane;
-    uint32_t a = ring_at<SWZ>(ring_s, idx);                   // this lane's word of the row
-    uint32_t b = a - ((SWZ && (idx & 31u) == 0) ? 8u : 4u);   // and its predecessor (not used for word 0): a pad between
+    uint32_t a = ring_at<SWZ>(ring_s, idx);                   // this lane's word of row 0
+    uint32_t b = a - ((SWZ && (idx & 31u) == 0) ? 8u : 4u);   // and its predecessor: a pad may lie between
     uint32_t *o = out + lane;
-#pragma unroll 1
-    for (uint32_t j = lane; j < cnt; j += 64u, a += 2u * kRow, b += 2u * kRow, o += 64) {
-        const bool two = j + 32u < cnt;
+    int left = (int)cnt - (int)lane;                          // words of this lane's column still to write: rows with 32 t < left
+    {
         const uint32_t c0 = lds_free(a);
-        const uint32_t b0 = j ? lds_free(b) : first_before;           // only word 0 lacks a staged predecessor
-        uint32_t c1 = 0, b1 = 0;
-        if (two) {
-            c1 = lds_free(a + kRow);
-            b1 = lds_free(b + kRow);
+        uint32_t b0 = lds_free(b);                            // (lane 0: some word before the chunk, never used)
+        if (lane == 0) b0 = first_before;
+        if (left > 0) __stcs(o, __funnelshift_r(c0, b0, sh)); // written once, never read here: stream it
+    }
+    uint32_t full = cnt >> 5;                                 // rows in which every lane has a word
+#pragma unroll 1
+    for (; full >= 5u; full -= 4u, left -= 128) {             // rows 1..4 are full
+        a += 4u * kRow, b += 4u * kRow, o += 128;
+        uint32_t c[4], p[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            c[t] = lds_free(a - (3u - t) * kRow);
+            p[t] = lds_free(b - (3u - t) * kRow);
         }
-        __stcs(o, __funnelshift_r(c0, b0, sh));                   // written once, never read here: stream it
-        if (two) __stcs(o + 32, __funnelshift_r(c1, b1, sh));
+#pragma unroll
+        for (int t = 0; t < 4; t++) __stcs(o - (3 - t) * 32, __funnelshift_r(c[t], p[t], sh));
+    }
+#pragma unroll
+    for (int t = 1; t <= 4; t++) {                            // rows 1..4 of what is left: full, ragged or absent
+        if (left > 32 * t)
+            __stcs(o + 32 * t, __funnelshift_r(lds_free(a + (uint32_t)t * kRow), lds_free(b + (uint32_t)t * kRow), sh));
     }
 }
 
@@ -837,6 +852,11 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
 #pragma unroll
             for (int g = 0; g < NG; g++) los[g] = gss[g] = 0;
         }
+#ifndef HB_NO_E2
+        // a lane that met an over-long group re-reads that group's input word in pass 2: start it on its way to L1 now
+        // (one 128-byte line holds the lane's 64 bytes), the scan and the ring bookkeeping hide the L2 latency
+        if (CHECK && G >= 4 && HB_UNLIKELY((ormask & ~31u) != 0u)) asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+#endif
         // Pass 1 has consumed `w`: request the next chunk now; it has the rest of this tile to arrive.  (One set
         // of input registers instead of two: measured +5-7 %, and no scoreboard aliasing between the two loads.)
         if (full_next) ld_lane(src + step, w);
@@ -929,6 +949,36 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         q = qn;
                         lo_prev = los[g];
                     }
+#ifndef HB_NO_E2
+                    // the group's symbols: G consecutive bytes of the lane's 64 -> at most ceil((G + 3) / 4) words, loaded
+                    // once (L1: prefetched after pass 1), then G lookups straight from registers
+                    constexpr int kGW = (G + 3) / 4;                     // G = 4: one word; 6, 8: two (S is a multiple of 4)
+                    const uint32_t w0i = (og * (uint32_t)G) >> 2;
+                    uint32_t gw[kGW];
+#pragma unroll
+                    for (int j = 0; j < kGW; j++) gw[j] = (w0i + j < (uint32_t)kLaneWords) ? __ldg(src + w0i + j) : 0u;
+#pragma unroll
+                    for (int j = 0; j < G; j++) {
+                        const uint32_t i = og * (uint32_t)G + (uint32_t)j;       // symbol index inside the lane
+                        if (i < (uint32_t)S) {
+                            const uint32_t rel = i - (w0i << 2);                      // 0 .. 4 kGW - 1
+                            uint32_t wv = gw[0];
+#pragma unroll
+                            for (int t = 1; t < kGW; t++) wv = (rel >> 2) == (uint32_t)t ? gw[t] : wv;
+                            const uint32_t sym = (wv >> ((3u - (rel & 3u)) * 8u)) & 0xFFu;
+                            uint32_t cwl, l;
+                            fetch_entry<WIDE>(tab_s, sym, lane, cwl, l);
+                            const uint32_t lo_new = __funnelshift_l(cwl, lo_s, l);
+                            const uint32_t qn = q_s + l;
+                            if ((qn ^ q_s) & 32u) {
+                                sts_u32(wa_s.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_s, 0u, l), qn));
+                                wa_s.next();
+                            }
+                            q_s = qn;
+                            lo_s = lo_new;
+                        }
+                    }
+#else
                     const unsigned char *lane_bytes = reinterpret_cast<const unsigned char *>(src);
 #pragma unroll 1
                     for (uint32_t i = og * (uint32_t)G; i < og * (uint32_t)G + (uint32_t)G && i < (uint32_t)S; i++) {
@@ -943,6 +993,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         q_s = qn;
                         lo_s = lo_new;
                     }
+#endif
                 }
             }
             const uint32_t r = q & 31u;
