@@ -263,6 +263,33 @@ __device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v)
 {
     asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// ---- checked build (tools/build_variant.sh checked -DHB_CHECKED; compute-sanitizer is closed on this pool): every
+// staging access must stay inside the worker's own ring, every output word inside the capacity, every input load
+// inside the buffer, every tree access inside the tree.  A violation prints and traps.
+#ifdef HB_CHECKED
+#define HB_ASSERT(cond, what)                                                                                   \
+    do {                                                                                                        \
+        if (!(cond)) {                                                                                          \
+            printf("HB_CHECKED violation: %s (block %d thread %d)\n", what, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                           \
+        }                                                                                                       \
+    } while (0)
+#else
+#define HB_ASSERT(cond, what) do { } while (0)
+#endif
+// a store / or-reduction into a worker's staging ring (physical bytes [ring_s, ring_s + kRingBytes))
+__device__ __forceinline__ void ring_sts(uint32_t ring_s, uint32_t addr, uint32_t v)
+{
+    HB_ASSERT(addr >= ring_s && addr + 4u <= ring_s + kRingBytes && (addr & 3u) == 0, "staging store outside the ring");
+    (void)ring_s;
+    sts_u32(addr, v);
+}
+__device__ __forceinline__ void ring_red_or(uint32_t ring_s, uint32_t addr, uint32_t v)
+{
+    HB_ASSERT(addr >= ring_s && addr + 4u <= ring_s + kRingBytes && (addr & 3u) == 0, "staging reduction outside the ring");
+    (void)ring_s;
+    red_or_shared(addr, v);
+}
 __device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t x, uint32_t y)
 {
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
@@ -520,6 +547,7 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
             bool pending = i != 0;
             for (;;) {
                 if (pending) {
+                    HB_ASSERT(i < p.n_tiles, "look-back beyond the tree");
                     v = ld_relaxed_u64(&p.tree[i]);
                     pending = (v & ~kTreeSumMask) != want;
                 }
@@ -672,6 +700,8 @@ __device__ __forceinline__ void copy_out(const EncParams &p, uint32_t ring_s, ui
     const unsigned long long g0 = (unsigned long long)rec.y << 32 | rec.x;
     if (HB_LIKELY(!(rec.w & kRecSlow))) {
         // common case: every word this chunk owns comes from two neighbouring staged words
+        HB_ASSERT(g0 + nfull <= p.out_cap_words, "copy-out beyond the output capacity");
+        HB_ASSERT(i0 + ((n + 31u) >> 5) <= kRingWords && nfull <= ((n + 31u) >> 5) + 1u, "copy-out beyond the staged chunk");
         copy_run<SWZ>(p.out + g0, ring_s, i0, nfull, rec.z, sh, lane);
     } else {
         // the job's final word(s), or an output buffer that is too small
@@ -714,7 +744,7 @@ __device__ __forceinline__ void redo_lane(const uint32_t *src, uint32_t laneoff,
             const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
             const uint32_t qn = q + l;
             if ((qn ^ q) & 32u) {
-                sts_u32(wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+                ring_sts(ring_s, wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
                 wa.next();
             }
             q = qn;
@@ -739,7 +769,7 @@ __device__ __forceinline__ void redo_lane_unrolled(const uint32_t *src, uint32_t
         const uint32_t lo_new = __funnelshift_l(cwl, lo_prev, l);
         const uint32_t qn = q + l;
         if ((qn ^ q) & 32u) {
-            sts_u32(wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
+            ring_sts(ring_s, wa.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_prev, 0u, l), qn));
             wa.next();
         }
         q = qn;
@@ -803,6 +833,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
     };
 
     uint32_t w[kLaneWords];
+    HB_ASSERT(!KF || (src + kLaneWords <= p.in + p.n_words), "input load beyond the buffer");
     if (KF) ld_lane(src, w);
 
     for (uint32_t k = 0; k < K; k++) {
@@ -859,6 +890,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
 #endif
         // Pass 1 has consumed `w`: request the next chunk now; it has the rest of this tile to arrive.  (One set
         // of input registers instead of two: measured +5-7 %, and no scoreboard aliasing between the two loads.)
+        HB_ASSERT(!full_next || (src + step + kLaneWords <= p.in + p.n_words), "input load beyond the buffer");
         if (full_next) ld_lane(src + step, w);
         if (p.l2_prefetch && k + 2u < KF) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2u * step));
         prof.add(kProfPass1, t0);
@@ -905,7 +937,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         // the 32 bits that end at the boundary: the low (qn & 31) of them come from the window
                         // before this group, the rest from the window after it (funnel shifts use qn mod 32)
                         const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);   // lo_prev >> (32 - gs)
-                        sts_u32(wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
+                        ring_sts(ring_s, wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
                         wa.next();
                     }
                     q = qn;
@@ -943,7 +975,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                             wa.skip((qn >> 5) - (q >> 5));
                         } else if ((qn ^ q) & 32u) {
                             const uint32_t hi = __funnelshift_l(lo_prev, 0u, gss[g]);
-                            sts_u32(wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
+                            ring_sts(ring_s, wa.addr(ring_s), __funnelshift_r(los[g], hi, qn));
                             wa.next();
                         }
                         q = qn;
@@ -971,7 +1003,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                             const uint32_t lo_new = __funnelshift_l(cwl, lo_s, l);
                             const uint32_t qn = q_s + l;
                             if ((qn ^ q_s) & 32u) {
-                                sts_u32(wa_s.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_s, 0u, l), qn));
+                                ring_sts(ring_s, wa_s.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_s, 0u, l), qn));
                                 wa_s.next();
                             }
                             q_s = qn;
@@ -987,7 +1019,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         const uint32_t lo_new = __funnelshift_l(cwl, lo_s, l);
                         const uint32_t qn = q_s + l;
                         if ((qn ^ q_s) & 32u) {
-                            sts_u32(wa_s.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_s, 0u, l), qn));
+                            ring_sts(ring_s, wa_s.addr(ring_s), __funnelshift_r(lo_new, __funnelshift_l(lo_s, 0u, l), qn));
                             wa_s.next();
                         }
                         q_s = qn;
@@ -999,13 +1031,13 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
             const uint32_t r = q & 31u;
             const uint32_t tailw = r ? (lo_prev << (32u - r)) : 0u;
             const uint32_t left_tail = __shfl_up_sync(0xFFFFFFFFu, tailw, 1);
-            if (lane != 0 && (q0 & 31u)) sts_u32(wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
-            if (lane == 31 && r) sts_u32(wa.addr(ring_s), tailw);                  // the word that holds bit n
+            if (lane != 0 && (q0 & 31u)) ring_sts(ring_s, wa0, lds_u32(wa0) | left_tail);   // my head word, completed by me
+            if (lane == 31 && r) ring_sts(ring_s, wa.addr(ring_s), tailw);                  // the word that holds bit n
         } else {
             const unsigned long long tile = tile0 + (unsigned long long)k * gridDim.x;
             const unsigned long long sym0 =
                 (tile * kW + warp) * (unsigned long long)(32 * S) + lane * (uint32_t)S;
-            for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) sts_u32(ring_at<SWZ>(ring_s, i0 + j), 0u);
+            for (uint32_t j = lane; j < ((n + 31u) >> 5); j += 32u) ring_sts(ring_s, ring_at<SWZ>(ring_s, i0 + j), 0u);
             __syncwarp();
             uint32_t q = q0, lo = 0;
 #pragma unroll 1
@@ -1017,7 +1049,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                         const uint32_t ln = __funnelshift_l(cwl, lo, l);
                         const uint32_t qn = q + l;
                         if ((qn ^ q) & ~31u)
-                            red_or_shared(ring_at<SWZ>(ring_s, i0 + (qn >> 5) - 1u),
+                            ring_red_or(ring_s, ring_at<SWZ>(ring_s, i0 + (qn >> 5) - 1u),
                                           __funnelshift_r(ln, __funnelshift_l(lo, 0u, l), qn));
                         q = qn;
                         lo = ln;
@@ -1025,7 +1057,7 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
                 }
             }
             const uint32_t f = q & 31u;
-            if (f) red_or_shared(ring_at<SWZ>(ring_s, i0 + (q >> 5)), lo << (32u - f));
+            if (f) ring_red_or(ring_s, ring_at<SWZ>(ring_s, i0 + (q >> 5)), lo << (32u - f));
         }
         __syncwarp();
         prof.add(kProfEmit, t0);

@@ -12,7 +12,10 @@ namespace hb {
 // ---- geometry of the single-pass encoder ---------------------------------------------------------
 // One persistent CTA per SM: kEncWorkers worker warps + a publisher warp + kEncResolvers resolver warps.  A tile is the CTA's unit of
 // work and of the look-back; a warp chunk (1/kEncWorkers of a tile) is a worker warp's unit.
-constexpr int kEncWorkers = 16;
+#ifndef HB_WORKERS
+#define HB_WORKERS 16                  // (8: the warp-count experiment of round 2)
+#endif
+constexpr int kEncWorkers = HB_WORKERS;
 #ifndef HB_RESOLVERS
 #define HB_RESOLVERS 2
 #endif
