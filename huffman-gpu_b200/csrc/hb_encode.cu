@@ -52,6 +52,8 @@
  *     per word to the global phase.  An output word that straddles two chunks belongs to the
  *     right-hand chunk: no atomics on the output and no memset of it.
  */
+#include <cstdio>
+
 #include "hb_kernels.cuh"
 
 #ifndef HB_WAIT_NS
