@@ -107,7 +107,15 @@ constexpr int kRingsBelow = 6;                          // rings that fit under 
 constexpr uint32_t kRingsBelowOffset = 0x2000 - kSmemReserved;
 constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
 constexpr uint32_t kCtrlOffset = 0;
+#ifdef HB_BULK_STORE
+// experiment ("plain vs TMA bulk stores"): a 1 KiB bounce buffer per worker behind the rings
+constexpr uint32_t kBounceWords = 256;
+constexpr uint32_t kBounceOffset = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
+constexpr uint32_t kSmemBytes = kBounceOffset + kW * kBounceWords * 4u;
+static_assert(kSmemBytes <= 227u * 1024u, "dynamic shared memory");
+#else
 constexpr uint32_t kSmemBytes = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
+#endif
 static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes <= kTabOffset, "rings 0..5 end before the table starts");
 // a chunk is staged contiguously (it never wraps) and must fit even when every symbol takes the longest code
 static_assert((uint32_t)S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
@@ -691,6 +699,45 @@ __device__ __forceinline__ void copy_run(uint32_t *out, uint32_t ring_s, uint32_
     }
 }
 
+#ifdef HB_BULK_STORE
+// The same copy through a bounce buffer and TMA bulk stores (cp.async.bulk.global.shared::cta): the words are shifted to
+// the output phase into the worker's bounce buffer, in pieces of up to 224, at the 16-byte phase of their global
+// address; the 16-byte-aligned body of a piece leaves as ONE bulk copy issued by lane 0, the up to three words
+// before and after it as plain stores.  The bounce buffer is reused only after the previous bulk copy has read it.
+template <bool SWZ>
+__device__ __forceinline__ void copy_run_bulk(uint32_t *out, uint32_t ring_s, uint32_t bounce_s, uint32_t i0, uint32_t cnt,
+                                              uint32_t first_before, uint32_t sh, uint32_t lane)
+{
+    constexpr uint32_t kPiece = 224u;                                  // 7 rows
+    for (uint32_t j0 = 0; j0 < cnt; j0 += kPiece) {
+        const uint32_t m = cnt - j0 < kPiece ? cnt - j0 : kPiece;
+        const uint32_t a = (uint32_t)((uintptr_t)(out + j0) >> 2) & 3u;          // word phase of the piece inside 16 bytes
+        const uint32_t head_n = (4u - a) & 3u;
+        const uint32_t body_n = m > head_n ? ((m - head_n) & ~3u) : 0u;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        for (uint32_t j = lane; j < m; j += 32u) {
+            const uint32_t idx = i0 + j0 + j;
+            const uint32_t cur = lds_free(ring_at<SWZ>(ring_s, idx));
+            const uint32_t before = (j0 + j) ? lds_free(ring_at<SWZ>(ring_s, idx - 1u)) : first_before;
+            const uint32_t v = __funnelshift_r(cur, before, sh);
+            if (j >= head_n && j < head_n + body_n)
+                sts_u32(bounce_s + (a + j) * 4u, v);
+            else
+                __stcs(out + j0 + j, v);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && body_n) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + j0 + head_n),
+                         "r"(bounce_s + (a + head_n) * 4u), "r"(body_n * 4u)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+#endif
+
 // The chunk (n bits) occupies the staged words i0 onwards of the ring (contiguous: chunks never wrap);
 // `rec` is the resolver's record for it.
 template <bool SWZ>
@@ -704,7 +751,12 @@ __device__ __forceinline__ void copy_out(const EncParams &p, uint32_t ring_s, ui
         // common case: every word this chunk owns comes from two neighbouring staged words
         HB_ASSERT(g0 + nfull <= p.out_cap_words, "copy-out beyond the output capacity");
         HB_ASSERT(i0 + ((n + 31u) >> 5) <= kRingWords && nfull <= ((n + 31u) >> 5) + 1u, "copy-out beyond the staged chunk");
+#ifdef HB_BULK_STORE
+        copy_run_bulk<SWZ>(p.out + g0, ring_s, kSmemReserved + kBounceOffset + (threadIdx.x >> 5) * kBounceWords * 4u, i0, nfull,
+                           rec.z, sh, lane);
+#else
         copy_run<SWZ>(p.out + g0, ring_s, i0, nfull, rec.z, sh, lane);
+#endif
     } else {
         // the job's final word(s), or an output buffer that is too small
         const bool last = (rec.w & kRecLast) != 0;
@@ -1084,6 +1136,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         wait_record();
         retire();
     }
+#ifdef HB_BULK_STORE
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#endif
     HB_STAMP(p, 5, warp == 0 && lane == 0);
     prof.add(kProfWorker, t_worker);
     prof.flush(p, lane);
@@ -1243,7 +1298,12 @@ EncVariant pick_variant(const uint32_t lens[256])
         }
         const double p_group = dist[32];
         const double groups_per_chunk = 32.0 * (double)((S + G - 1) / G);
-        if (p_group * groups_per_chunk <= 0.02) {
+        // Expected over-long groups per chunk that a group size may cost.  Measured round 2 (cheaper detours): on the
+        // 8 GiB H 4.0 input G = 4 with 0.145 such groups per chunk beats G = 3 with none by 1.3 % (6 groups fewer to test,
+        // plain ring); on the H 2.2 input G = 6 with 0.23 loses 6.7 % against G = 4 with 0.01 (a detour is worth about 200-
+        // 300 issue slots).  The implied probabilities underestimate the tail of skewed data (x 7 on H 2.2 at G = 6), so
+        // the large groups keep the strict bound.
+        if (p_group * groups_per_chunk <= (G <= 4 ? 0.13 : 0.02)) {
             v.group = G;
             v.check = true;
             return v;

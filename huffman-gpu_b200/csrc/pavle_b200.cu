@@ -3,7 +3,7 @@
  * (main_test_cu.cu:41-180 main/runVLCTest, load_data.h:8-58 loadData; `./pavle data/test1024_H2.206587175259.in`),
  * on top of the C ABI of libhuffb200.so.  SURVEY.md section 8 f-1.
  *
- *   pavle_b200 <file> [--repeats N] [--no-check]
+ *   pavle_b200 <file> [--repeats N] [--no-check] [--cpu-lib <shared library exporting cpu_vlc_encode>]
  *
  * file -> device -> byte histogram (hb_histogram) -> Huffman codebook (hb_build_codebook) -> single-pass encode
  * (hb_encode_async, mean of N launches between CUDA events, as the reference times NT = 10 launches,
@@ -13,13 +13,20 @@
  * driver does not carry a second encoder: it DECODES the GPU stream on the host with the same tables and compares the
  * symbols with the file (a round trip), and checks the bit count against sum(hist[s] * len[s]).  Exit status 0 = PASS.
  * There is no CPU encode path here: without an sm_100 device hb_init fails and so does the driver.
+ *
+ * --cpu-lib: the reference's two CPU fields ("CPU Encoding time (CPU)", "CPU Encoded to %d [B]", main_test_cu.cu:120-125)
+ * and its own verdict, compare_vectors over ceil(bytes/4) words (main_test_cu.cu:126,171; comparison_helpers.h:5-16), for
+ * callers who have a cpu_vlc_encode at hand (e.g. the reference's cpuencode.cpp built as a shared library).  The
+ * library is dlopen()ed at run time and never linked: the product carries no CPU encoder.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/time.h>
 
 #include "../../include/huffman_b200.h"
 
@@ -91,11 +98,13 @@ static long long decode_and_compare(const uint32_t *stream, uint64_t total_bits,
 
 int main(int argc, char **argv)
 {
-    const char *path = NULL;
+    const char *path = NULL, *cpu_lib = NULL;
     int repeats = 10, check = 1;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--repeats") && i + 1 < argc)
             repeats = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--cpu-lib") && i + 1 < argc)
+            cpu_lib = argv[++i];
         else if (!strcmp(argv[i], "--no-check"))
             check = 0;
         else if (argv[i][0] != '-' && !path)
@@ -105,7 +114,7 @@ int main(int argc, char **argv)
     }
     if (!path || repeats < 1) {
         printf("No input file\n");                               /* load_data.h:27 */
-        fprintf(stderr, "usage: pavle_b200 <file> [--repeats N] [--no-check]   (%s)\n", hb_version());
+        fprintf(stderr, "usage: pavle_b200 <file> [--repeats N] [--no-check] [--cpu-lib lib.so]   (%s)\n", hb_version());
         return 2;
     }
 
@@ -156,8 +165,36 @@ int main(int argc, char **argv)
     printf("Parameters: num_elements: %llu, max code length: %d, tile: %u bytes, kernel: %s\n----------------------------\n",
            (unsigned long long)n_words, max_len, hb_tile_bytes(), hb_encode_variant(codewordlens));
 
-    /* ---- encode: warm-up, then the mean of `repeats` launches between events (main_test_cu.cu:136-156) ---- */
     const uint64_t cap_words = bits_expected / 32 + 2;
+
+    /* ---- optional: the caller's CPU encoder, timed as the reference times it (main_test_cu.cu:32-36,120-125) ---- */
+    uint32_t *cref = NULL;
+    unsigned int refbytesize = 0;
+    if (cpu_lib) {
+        typedef void (*cpu_fn)(unsigned int *, unsigned int, unsigned int *, unsigned int *, unsigned int *, unsigned int *);
+        void *h = dlopen(cpu_lib, RTLD_NOW | RTLD_LOCAL);
+        cpu_fn cpu = h ? (cpu_fn)dlsym(h, "cpu_vlc_encode") : NULL;
+        if (!cpu) {
+            fprintf(stderr, "%s: no cpu_vlc_encode (%s)\n", cpu_lib, dlerror());
+            return 2;
+        }
+        if (n_words >> 32) {
+            fprintf(stderr, "cpu_vlc_encode counts words in 32 bits (cpuencode.h:4-7): input too large for --cpu-lib\n");
+            return 2;
+        }
+        cref = (uint32_t *)calloc(cap_words + 1, 4);
+        if (!cref) return 3;
+        struct timeval tv;
+        gettimeofday(&tv, NULL);
+        const long long t0 = tv.tv_sec * 1000000LL + tv.tv_usec;
+        cpu((unsigned int *)source, (unsigned int)n_words, cref, &refbytesize, codewords, codewordlens);
+        gettimeofday(&tv, NULL);
+        const float msec = (float)((tv.tv_sec * 1000000LL + tv.tv_usec - t0) / 1000.0);
+        printf("CPU Encoding time (CPU): %f (ms)\n", msec);
+        printf("CPU Encoded to %d [B]\n", refbytesize);
+    }
+
+    /* ---- encode: warm-up, then the mean of `repeats` launches between events (main_test_cu.cu:136-156) ---- */
     uint32_t *d_out = NULL;
     CK(cudaMalloc(&d_out, cap_words * 4));
     uint64_t bits = 0;
@@ -195,7 +232,23 @@ int main(int argc, char **argv)
         free(stream);
         free(node);
     }
+    if (ok && cref) {
+        /* compare_vectors(crefData, destData, num_ints) with num_ints = ceil(refbytesize / 4): main_test_cu.cu:126,171 */
+        const uint64_t num_ints = (bits + 31) / 32;              /* (refbytesize itself wraps at 4 GiB, cpuencode.cpp:45) */
+        uint32_t *stream = (uint32_t *)malloc(cap_words * 4);
+        if (!stream) return 3;
+        CK(cudaMemcpy(stream, d_out, cap_words * 4, cudaMemcpyDeviceToHost));
+        ok = refbytesize == (unsigned int)((bits + 7) / 8);
+        for (uint64_t i = 0; ok && i < num_ints; i++)
+            if (stream[i] != cref[i]) {
+                printf("Error at word %llu: CPU %08x GPU %08x\n", (unsigned long long)i, cref[i], stream[i]);
+                ok = 0;
+            }
+        free(stream);
+        if (ok) printf("PASS! vectors are matching!\n");        /* comparison_helpers.h:13 */
+    }
     printf(ok ? "PASS!\n" : "FAIL!\n");
+    free(cref);
 
     cudaFree(d_out);
     cudaFree(d_in);

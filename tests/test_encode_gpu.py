@@ -560,3 +560,12 @@ def test_cli_driver_on_the_fixture_and_a_ragged_file(hb, tmp_path):
     ragged.write_bytes(rng.choice(256, size=3 * TILE + 4 * 37 + 3, p=np.r_[0.7, np.full(255, 0.3 / 255)]).astype(np.uint8).tobytes())
     out = subprocess.run([cli, str(ragged), "--repeats", "3"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "PASS!" in out.stdout, out.stdout + out.stderr
+    # the reference's CPU fields and its word-by-word compare (main_test_cu.cu:120-126,171), with the unmodified
+    # cpu_vlc_encode handed in as a shared library (test infrastructure: oracle/_ref); the driver links no CPU encoder
+    from conftest import ROOT
+    cpu_lib = os.path.join(ROOT, "oracle", "_ref", "libref.so")
+    if os.path.exists(cpu_lib):
+        out = subprocess.run([cli, str(fixture), "--cpu-lib", cpu_lib], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "CPU Encoded to 291334 [B]" in out.stdout and "CPU Encoding time (CPU):" in out.stdout
+        assert "PASS! vectors are matching!" in out.stdout
