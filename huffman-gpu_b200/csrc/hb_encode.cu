@@ -100,10 +100,20 @@ constexpr uint32_t kTabOffset = kTabWindow - kSmemReserved;          // offsets 
 #define HB_DEPTH 16
 #endif
 constexpr int kDepth = HB_DEPTH;                               // tiles a CTA may hold between encode and copy-out
+#ifdef HB_SMALL_RING_EXPERIMENT
+// experiment only ("TMA-staged loads"): half-size rings make room for two 2 KiB input stages per
+// worker; the same rings without the stages are the control.  NOT safe for codebooks whose chunks can outgrow 1024 words.
+constexpr uint32_t kRingWords = 1024;
+#else
 constexpr uint32_t kRingWords = 2048;                   // per worker, addressed modulo (power of two)
+#endif
 constexpr uint32_t kRingBytes = (kRingWords + kRingWords / 32) * 4;     // physical: room for one pad word per 32 (ring_at)
 constexpr uint32_t kRingMask = kRingWords - 1;
+#ifdef HB_SMALL_RING_EXPERIMENT
+constexpr int kRingsBelow = 13;
+#else
 constexpr int kRingsBelow = 6;                          // rings that fit under the table
+#endif
 constexpr uint32_t kRingsBelowOffset = 0x2000 - kSmemReserved;
 constexpr uint32_t kRingsAboveOffset = kTabOffset + kTabBytes;
 constexpr uint32_t kCtrlOffset = 0;
@@ -113,12 +123,20 @@ constexpr uint32_t kBounceWords = 256;
 constexpr uint32_t kBounceOffset = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
 constexpr uint32_t kSmemBytes = kBounceOffset + kW * kBounceWords * 4u;
 static_assert(kSmemBytes <= 227u * 1024u, "dynamic shared memory");
+#elif defined(HB_BULK_LOAD)
+// experiment: two input stages of one chunk (2 KiB) per worker behind the rings, and their two "full" mbarriers
+constexpr uint32_t kInOffset = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
+constexpr uint32_t kInBarOffset = kInOffset + kW * 2u * (uint32_t)kChunkBytes;
+constexpr uint32_t kSmemBytes = kInBarOffset + kW * 16u;
+static_assert(kSmemBytes <= 227u * 1024u, "dynamic shared memory");
 #else
 constexpr uint32_t kSmemBytes = kRingsAboveOffset + (kW - kRingsBelow) * kRingBytes;
 #endif
-static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes <= kTabOffset, "rings 0..5 end before the table starts");
+static_assert(kRingsBelowOffset + kRingsBelow * kRingBytes <= kTabOffset, "the lower rings end before the table starts");
+#ifndef HB_SMALL_RING_EXPERIMENT
 // a chunk is staged contiguously (it never wraps) and must fit even when every symbol takes the longest code
 static_assert((uint32_t)S * 31u + 2u <= kRingWords, "a ring must hold one worst-case chunk");
+#endif
 
 
 // Control block at the start of the dynamic block.  Everything in it is addressed through the shared WINDOW
@@ -153,7 +171,10 @@ __device__ __forceinline__ uint32_t ring_window(uint32_t w)
 }
 
 // Kernels for long codes (small G) stage with the padded ring layout.
-__host__ __device__ constexpr bool swizzled(int group) { return group <= 3; }
+#ifndef HB_SWZ_MAXG
+#define HB_SWZ_MAXG 3
+#endif
+__host__ __device__ constexpr bool swizzled(int group) { return group <= HB_SWZ_MAXG; }
 // Window address of logical word `idx` (< kRingWords) of a ring.  SWZ: one pad word after every 32.  A lane's write
 // position in pass 2 is about (bits per symbol) * 2 words per lane: at 4 or 8 bits per symbol the lanes are 8 or 16
 // words apart and a plain layout puts the stores of a warp into 4 or 2 banks; with the pad they fall into 32.
@@ -887,8 +908,33 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
     };
 
     uint32_t w[kLaneWords];
+#ifdef HB_BULK_LOAD
+    // TMA-staged loads: lane 0 asks for whole chunks (cp.async.bulk, 2 KiB, completion on an mbarrier) two chunks ahead,
+    // into two stages in shared memory; every lane then takes its 64 bytes with four 128-bit shared loads
+    const uint32_t in_s = kSmemReserved + kInOffset + warp * 2u * (uint32_t)kChunkBytes;
+    const uint32_t inbar_s = kSmemReserved + kInBarOffset + warp * 16u;
+    const uint32_t *chunk_g = p.in + (tile0 * kW + warp) * (unsigned long long)kChunkWords;     // the warp's chunk of its tile 0
+    auto request = [&](uint32_t kk) {           // lane 0: chunk kk of this worker -> stage kk & 1
+        const uint32_t bar = inbar_s + (kk & 1u) * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)kChunkBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         in_s + (kk & 1u) * (uint32_t)kChunkBytes),
+                     "l"(chunk_g + (unsigned long long)kk * step), "r"((uint32_t)kChunkBytes), "r"(bar)
+                     : "memory");
+    };
+    if (lane == 0) {
+        mbar_init(inbar_s, 1);
+        mbar_init(inbar_s + 8u, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (KF > 0u) request(0);
+        if (KF > 1u) request(1);
+    }
+    __syncwarp();
+#else
     HB_ASSERT(!KF || (src + kLaneWords <= p.in + p.n_words), "input load beyond the buffer");
     if (KF) ld_lane(src, w);
+#endif
 
     for (uint32_t k = 0; k < K; k++) {
         const uint32_t slot = slot_of(k);
@@ -899,6 +945,16 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         uint32_t los[NG], gss[NG];
         uint32_t bt = 0, ormask = 0;
         if (HB_LIKELY(full)) {
+#ifdef HB_BULK_LOAD
+            mbar_wait(inbar_s + (k & 1u) * 8u, (k >> 1) & 1u);
+#pragma unroll
+            for (int j = 0; j < kLaneWords; j += 4) {
+                const uint4 v = lds_u128(in_s + (k & 1u) * (uint32_t)kChunkBytes + lane * (uint32_t)(kLaneWords * 4) + (uint32_t)j * 4u);
+                w[j] = v.x, w[j + 1] = v.y, w[j + 2] = v.z, w[j + 3] = v.w;
+            }
+            __syncwarp();                                      // every lane has read the stage: it may be refilled
+            if (lane == 0 && k + 2u < KF) request(k + 2u);
+#endif
             uint32_t lo = 0, gs = 0;
 #pragma unroll
             for (int i = 0; i < S; i++) {
@@ -944,8 +1000,10 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
 #endif
         // Pass 1 has consumed `w`: request the next chunk now; it has the rest of this tile to arrive.  (One set
         // of input registers instead of two: measured +5-7 %, and no scoreboard aliasing between the two loads.)
+#if !defined(HB_LATE_LOAD) && !defined(HB_BULK_LOAD)
         HB_ASSERT(!full_next || (src + step + kLaneWords <= p.in + p.n_words), "input load beyond the buffer");
         if (full_next) ld_lane(src + step, w);
+#endif
         if (p.l2_prefetch && k + 2u < KF) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + 2u * step));
         prof.add(kProfPass1, t0);
         t0 = prof.now();
@@ -1116,6 +1174,9 @@ __device__ void worker(const EncParams &p, uint32_t tab_s, uint32_t ring_s, uint
         __syncwarp();
         prof.add(kProfEmit, t0);
 
+#ifdef HB_LATE_LOAD
+        if (full_next) ld_lane(src + step, w);                 // (experiment: the next chunk requested after pass 2)
+#endif
         // ---------------- the chunk is staged ----------------
         if (lane == 0) mbar_arrive(kBarStagedS + slot * 8u);
         head += need;

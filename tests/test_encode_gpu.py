@@ -370,6 +370,65 @@ def test_non_default_stream(hb, enc, orc, torch_mod):
         check_against_oracle(orc, enc, torch_mod, data, cw, cl)
 
 
+def test_jobs_on_alternating_streams_share_one_context(hb, enc, orc, torch_mod):
+    """A context serialises its jobs (they share the device table, the result block and the two alternating look-back
+    trees): asynchronous jobs handed alternately to two streams, with different codebooks, must each equal the oracle
+    (nothing ordered job B's table upload and tree reset behind job A's kernel on another stream)."""
+    rng = np.random.default_rng(11)
+    s1, s2 = torch_mod.cuda.Stream(), torch_mod.cuda.Stream()
+    jobs = []
+    for i in range(8):
+        nsym = [4, 64, 200, 17][i % 4]
+        data = rng.integers(0, nsym, size=TILE * (20 + i) + 4 * i, dtype=np.uint8)
+        cw, cl, _ = hb.build_codebook(orc.histogram(data))
+        ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
+        d_in = torch_mod.from_numpy(data).cuda()
+        d_out = torch_mod.full((ref_words.size + 2,), 0x5A5A5A5A, dtype=torch_mod.int32, device="cuda")
+        jobs.append((d_in, d_out, cw, cl, ref_words, ref_bits))
+    torch_mod.cuda.synchronize()
+    for i, (d_in, d_out, cw, cl, ref_words, ref_bits) in enumerate(jobs):
+        with torch_mod.cuda.stream(s1 if i % 2 == 0 else s2):
+            enc.encode_async(d_in, cw, cl, d_out)                      # no fetch in between: the jobs queue up
+    torch_mod.cuda.synchronize()
+    with torch_mod.cuda.stream(s2):
+        assert enc.encode_result() == jobs[-1][5]
+    for d_in, d_out, cw, cl, ref_words, ref_bits in jobs:
+        got = d_out.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got[: ref_words.size], ref_words)
+
+
+def test_job_size_limit(hb):
+    """a look-back tree node counts tiles in 22 bits: contexts for more than 2^21 tiles (64 GiB) are refused"""
+    import ctypes as C
+    ctx = hb.capi.vp()
+    rc = hb.lib().hb_init(C.byref(ctx), 0, (1 << 21) * 8192 + 1)
+    assert rc == hb.capi.HB_ERR_CAPACITY and not ctx.value
+
+
+def test_repeated_launches_are_deterministic(hb, enc, orc, torch_mod):
+    """200 back-to-back launches of one job (no host synchronisation in between), each into a freshly poisoned buffer:
+    every stream must have the oracle's checksums.  The kernel's hand-offs are relaxed atomics, mbarriers and plain
+    shared-memory stores ordered by them; a race would show up as a sporadic mismatch (compute-sanitizer's racecheck
+    is not available on this pool)."""
+    from huffman_gpu_b200.streamsum import stream_sums
+    wl = hb.workloads.get("c2", n_bytes=48 << 20)
+    data = orc.synth_fill(0, wl.n_bytes, wl.seed, wl.mode, wl.nbits, wl.thr)
+    cw, cl, _ = hb.build_codebook(orc.histogram(data))
+    ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
+    want = stream_sums(ref_words)
+    d_in = torch_mod.from_numpy(data).cuda()
+    outs = [torch_mod.empty(ref_words.size + 2, dtype=torch_mod.int32, device="cuda") for _ in range(8)]
+    for rep in range(25):
+        for o in outs:
+            o.fill_(0x5A5A5A5A)
+        for o in outs:
+            enc.encode_async(d_in, cw, cl, o)
+        assert enc.encode_result() == ref_bits
+        for o in outs:
+            assert stream_sums(o, ref_words.size) == want, rep
+            assert int(o[ref_words.size].item()) == 0x5A5A5A5A
+
+
 # ---- host-buffer entry points (the reference-facing call) ---------------------------------------------------
 def test_vlc_encode_drop_in_signature(hb, orc, ref, c1):
     """hb_vlc_encode(indata, num_elements, outdata, &outsize, codewords, codewordlens), host pointers."""
