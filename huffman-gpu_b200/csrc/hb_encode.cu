@@ -504,12 +504,14 @@ __device__ void publisher(const EncParams &p, uint32_t lane, uint32_t K)
         mbar_wait(kBarSumsS + slot * 8u, par_of(k));
         const uint32_t n = (lane < (uint32_t)kW) ? lds_u32(kChunkS + (slot * kW + lane) * 8u + 4u) : 0u;
         const uint32_t btile = __reduce_add_sync(0xFFFFFFFFu, n);
-        // Fenwick update: lane j adds {1 tile, btile bits} to the j-th node above tile t_cur (1-based index
-        // t_cur + 1, then repeatedly + lowbit).  Nodes at or beyond the last tile are never read: skip them.
+        // Fenwick update: {1 tile, btile bits} goes to every node above tile t_cur (1-based index x = t_cur + 1, then
+        // repeatedly + lowbit).  In closed form: lane b owns x rounded up to a multiple of 2^b, and that is a node of the
+        // chain iff its bit b is set (its lowbit is then 2^b) -- no loop.  Nodes at or beyond the last tile are never
+        // read: skip them.  (Tile indices fit 32 bits: kMaxJobTiles.)
         {
-            unsigned long long i = t_cur + 1ULL;
-            for (uint32_t j = 0; j < lane && i < p.n_tiles; j++) i += i & (0ULL - i);
-            if (i < p.n_tiles) red_add_u64(&p.tree[i], kTreeOne | (unsigned long long)btile);
+            const uint32_t x = (uint32_t)t_cur + 1u, m = (1u << lane) - 1u;
+            const uint32_t i = (x + m) & ~m;
+            if (((i >> lane) & 1u) && i < p.n_tiles) red_add_u64(&p.tree[i], kTreeOne | (unsigned long long)btile);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(kBarAggS + slot * 8u);
@@ -567,13 +569,14 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
         prof.count(kProfTiles);
 
         // ---------------- look-back: the <= log2(n) tree nodes that tile the prefix [0, tile) ----------------
-        // lane j owns node i_j (i_0 = tile, i_{j+1} = i_j - lowbit(i_j)), final once it has counted lowbit(i_j) tiles
+        // the nodes that tile the prefix [0, tile): for every set bit b of `tile`, the node `tile` with the bits below b
+        // cleared, which covers 2^b tiles (lane b owns it: closed form, no loop); final once it has counted them all
         t0 = prof.now();
         unsigned long long excl = 0;
         {
-            unsigned long long i = tile;
-            for (uint32_t j = 0; j < lane && i; j++) i &= i - 1ULL;
-            const unsigned long long want = (i & (0ULL - i)) << kTreeCountShift;
+            const uint32_t tl = (uint32_t)tile;
+            const unsigned long long i = ((tl >> lane) & 1u) ? (unsigned long long)((tl >> lane) << lane) : 0ULL;
+            const unsigned long long want = (unsigned long long)(1u << lane) << kTreeCountShift;
             unsigned long long v = 0;
             bool pending = i != 0;
             for (;;) {
