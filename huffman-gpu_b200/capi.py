@@ -60,6 +60,8 @@ SIGNATURES = {
     "hb_stitch_close": (C.c_int, [vp]),
     "hb_shard_offsets": (C.c_int, [u64p, C.c_int, u64p, u64p]),
     "hb_stitch_seam": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
+    "hb_encode_tile_index": (C.c_int, [vp, C.c_uint64, vp, vp]),
+    "hb_decode": (C.c_int, [vp, vp, C.c_uint64, vp, C.c_uint64, u32p, u32p, vp, vp]),
     "hb_synth_fill": (C.c_int, [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, u32p,
                                 C.c_int, u8p, vp]),
     "hb_tile_bytes": (C.c_uint32, []),

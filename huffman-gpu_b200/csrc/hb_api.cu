@@ -383,6 +383,10 @@ void hb_free(hb_ctx *ctx)
     cudaFree(ctx->d_symmap);
     cudaFree(ctx->d_in_buf);
     cudaFree(ctx->d_out_buf);
+    cudaFree(ctx->d_dec_lut);
+    cudaFree(ctx->d_dec_trie);
+    cudaFree(ctx->d_dec_error);
+    if (ctx->h_dec_stage) cudaFreeHost(ctx->h_dec_stage);
     if (ctx->table_uploaded) cudaEventDestroy(ctx->table_uploaded);
     if (ctx->job_done) cudaEventDestroy(ctx->job_done);
     for (int i = 0; i < kMaxChunks; i++) {
@@ -458,6 +462,10 @@ int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const u
     ctx->pending = true;
     ctx->pending_empty = false;
     ctx->pending_start_bit = start_bit;
+    ctx->last_job_tiles = tiles_of(n_words);
+    ctx->last_job_words = n_words;
+    ctx->last_job_start_bit = start_bit;
+    ctx->last_job_valid = true;
     return HB_OK;
 }
 
@@ -536,6 +544,7 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
     }
     if ((rc = order_after_previous_job(ctx, st)) != HB_OK) return rc;
     if ((rc = set_codebook(ctx, codewords, codewordlens, st)) != HB_OK) return rc;
+    ctx->last_job_valid = false;               // (hb_encode_tile_index describes device-buffer jobs only)
     memset(ctx->h_result, 0, kMaxChunks * sizeof(hb::EncResult));
 
     uint64_t bits = 0;
@@ -623,6 +632,79 @@ int hb_vlc_encode_host(hb_ctx *ctx, const uint32_t *h_in, uint64_t n_words, uint
     if (total_bits) *total_bits = bits;
     if (out_bytes) *out_bytes = (bits + 7) / 8;
     return HB_OK;
+}
+
+// ---- decoder -----------------------------------------------------------------------
+int hb_encode_tile_index(hb_ctx *ctx, uint64_t total_bits, uint64_t *d_tile_bits, void *stream)
+{
+    if (!ctx || !d_tile_bits) return HB_ERR_ARG;
+    if (!ctx->last_job_valid || ctx->pending) return HB_ERR_STATE;      // after hb_encode / hb_encode_result, before the next job
+    DeviceGuard g(ctx->device);
+    HB_CUDA(ctx, hb::launch_tile_index(ctx->d_tree[ctx->tree_cur], ctx->last_job_tiles, ctx->last_job_start_bit,
+                                       ctx->last_job_start_bit + total_bits, (unsigned long long *)d_tile_bits,
+                                       (cudaStream_t)stream));
+    ctx->launches++;
+    return HB_OK;
+}
+
+int hb_decode(hb_ctx *ctx, const uint32_t *d_stream, uint64_t stream_words, const uint64_t *d_tile_bits, uint64_t n_words,
+              const uint32_t codewords[256], const uint32_t codewordlens[256], uint32_t *d_out, void *stream)
+{
+    if (!ctx || !codewords || !codewordlens || (n_words && (!d_stream || !d_tile_bits || !d_out))) return HB_ERR_ARG;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int kLut = 1 << hb::kDecLutBits;
+    if (!ctx->d_dec_lut) {
+        HB_CUDA(ctx, cudaMalloc(&ctx->d_dec_lut, kLut * sizeof(uint16_t)));
+        HB_CUDA(ctx, cudaMalloc(&ctx->d_dec_trie, 1024 * sizeof(int16_t)));
+        HB_CUDA(ctx, cudaMalloc(&ctx->d_dec_error, sizeof(unsigned long long)));
+        HB_CUDA(ctx, cudaMallocHost(&ctx->h_dec_stage, kLut * sizeof(uint16_t) + 1024 * sizeof(int16_t) + 16));
+    }
+    // the code trie (every used code must be a leaf: a prefix code) and the table of the codes of up to kDecLutBits bits
+    uint16_t *lut = (uint16_t *)ctx->h_dec_stage;
+    int16_t *trie = (int16_t *)(lut + kLut);
+    unsigned long long *h_err = (unsigned long long *)(trie + 1024);
+    HB_CUDA(ctx, cudaStreamSynchronize(st));                  // (the staging block may still feed an earlier decode)
+    memset(lut, 0, kLut * sizeof(uint16_t));
+    memset(trie, 0, 1024 * sizeof(int16_t));
+    int used = 1;
+    for (int s = 0; s < 256; s++) {
+        const uint32_t l = codewordlens[s];
+        if (!l) continue;
+        if (l > HB_MAX_CODE_LEN) return HB_ERR_CODELEN;
+        if (codewords[s] >> l) return HB_ERR_CODEWORD;
+        int cur = 0;
+        for (int b = (int)l - 1; b >= 0; b--) {
+            const int bit = (int)((codewords[s] >> b) & 1u);
+            int16_t &slot = trie[cur * 2 + bit];
+            if (b == 0) {
+                if (slot != 0) return HB_ERR_CODEWORD;           // not a prefix code
+                slot = (int16_t)(-(s + 1));
+            } else {
+                if (slot < 0) return HB_ERR_CODEWORD;
+                if (slot == 0) {
+                    if (used >= 512) return HB_ERR_CODEWORD;
+                    slot = (int16_t)used++;
+                }
+                cur = slot;
+            }
+        }
+        if (l <= (uint32_t)hb::kDecLutBits) {
+            const uint32_t base = codewords[s] << (hb::kDecLutBits - l), span = 1u << (hb::kDecLutBits - l);
+            for (uint32_t i = 0; i < span; i++) lut[base + i] = (uint16_t)(s | (l << 8));
+        }
+    }
+    if (n_words == 0) return HB_OK;
+    *h_err = 0;
+    HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_dec_lut, lut, kLut * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+    HB_CUDA(ctx, cudaMemcpyAsync(ctx->d_dec_trie, trie, 1024 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    HB_CUDA(ctx, cudaMemsetAsync(ctx->d_dec_error, 0, sizeof(unsigned long long), st));
+    HB_CUDA(ctx, hb::launch_decode(d_stream, (const unsigned long long *)d_tile_bits, tiles_of(n_words), n_words * 4, stream_words,
+                                   ctx->d_dec_lut, ctx->d_dec_trie, d_out, ctx->d_dec_error, st));
+    ctx->launches++;
+    HB_CUDA(ctx, cudaMemcpyAsync(h_err, ctx->d_dec_error, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    HB_CUDA(ctx, cudaStreamSynchronize(st));
+    return *h_err ? HB_ERR_CODEWORD : HB_OK;                  // a tile did not end where the next one starts: not this stream's tables
 }
 
 static hb_ctx *g_default_ctx = nullptr;

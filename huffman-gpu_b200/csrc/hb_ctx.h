@@ -55,6 +55,15 @@ struct hb_ctx {
     cudaEvent_t ev_chunk[kMaxChunks] = {};            // one per launch of a chunked host job
     cudaEvent_t ev_h2d[kMaxChunks] = {};              // ... and one per input copy
 
+    // decoder (hb_decode): device copies of the decode table and the code trie, an error counter; the job the trees
+    // still describe (hb_encode_tile_index)
+    uint16_t *d_dec_lut = nullptr;
+    int16_t *d_dec_trie = nullptr;
+    unsigned long long *d_dec_error = nullptr;
+    void *h_dec_stage = nullptr;              // pinned staging for the two tables + the error word
+    uint64_t last_job_tiles = 0, last_job_words = 0, last_job_start_bit = 0;
+    bool last_job_valid = false;
+
     unsigned long long *d_prof = nullptr;     // $HB_PROFILE: kernel cycle counters, dumped by hb_free
     uint64_t launches = 0;
     int last_cuda = 0;

@@ -80,7 +80,7 @@ constexpr int kSlotStride = 256;                        // table stride per symb
 constexpr int kTabBytes = 256 * kSlotStride;            // 64 KiB
 // Fenwick node = [63:42] tiles counted | [41:0] bits summed; jobs are limited to kMaxJobTiles tiles (hb_init and
 // launch_tiles reject larger ones) so that neither field can overflow
-constexpr int kTreeCountShift = 42;
+// (kTreeCountShift: hb_kernels.cuh -- the tile index of the decoder reads the same nodes)
 static_assert(kMaxJobTiles <= (1ULL << (64 - kTreeCountShift - 1)), "a node's tile count must fit its field");
 static_assert(kMaxJobTiles * (unsigned long long)kTileBytes * 31ULL < (1ULL << kTreeCountShift), "a node's bit sum must fit its field");
 constexpr unsigned long long kTreeOne = 1ULL << kTreeCountShift;

@@ -31,6 +31,7 @@ constexpr int kTileWords = kTileBytes / 4;
 // A look-back tree node counts tiles in 22 bits and sums bits in 42 (hb_encode.cu): a job has at most 2^21 tiles
 // (64 GiB of input; a node then counts at most 2^20 tiles and sums at most 64 GiB * 31 bits < 2^42).
 constexpr unsigned long long kMaxJobTiles = 1ULL << 21;
+constexpr int kTreeCountShift = 42;                                   // node = [63:42] tiles counted | [41:0] bits summed
 
 // Written by the kernel into mapped pinned host memory (zero-copy), read by the host after sync.
 struct EncResult {
@@ -82,6 +83,14 @@ cudaError_t launch_histogram(const uint32_t *d_in, unsigned long long n_words,
                              cudaStream_t stream);
 cudaError_t launch_or_words(uint32_t *d_dst, const uint32_t *d_src, unsigned long long n_words,
                             cudaStream_t stream);
+// decoder (hb_decode.cu): per-tile bit offsets from the look-back tree an encode left behind,
+// and the tile-parallel table/trie decoder
+cudaError_t launch_tile_index(const unsigned long long *d_tree, unsigned long long n_tiles, unsigned long long start_bit,
+                              unsigned long long end_bit, unsigned long long *d_tile_bits, cudaStream_t stream);
+cudaError_t launch_decode(const uint32_t *d_stream, const unsigned long long *d_tile_bits, unsigned long long n_tiles,
+                          unsigned long long n_symbols, unsigned long long n_stream_words, const uint16_t *d_lut,
+                          const int16_t *d_trie, uint32_t *d_out_words, unsigned long long *d_error, cudaStream_t stream);
+constexpr int kDecLutBits = 10;                                       // primary decode table: 2^10 entries of {symbol, length}
 cudaError_t launch_synth(uint8_t *d_out, unsigned long long first, unsigned long long n,
                          unsigned long long seed, int mode, int nbits, const uint32_t *d_thr, int K,
                          const uint8_t *d_symmap, cudaStream_t stream);

@@ -194,6 +194,21 @@ class Encoder:
                "hb_vlc_encode_host", self._ctx)
         return int(tb.value), int(ob.value)
 
+    def tile_index(self, total_bits, d_tile_bits):
+        """bit offsets of the tiles of the last encode job -> d_tile_bits (torch int64[n_tiles + 1])"""
+        _check(lib().hb_encode_tile_index(self._ctx, int(total_bits), d_tile_bits.data_ptr(), self._stream()),
+               "hb_encode_tile_index", self._ctx)
+
+    def decode(self, d_stream, d_tile_bits, codewords, codewordlens, d_out):
+        """the decoder (no reference equivalent): d_stream (int32 words) -> d_out (the encoder's input, any 4-byte
+        or byte tensor of the right size)"""
+        sptr, swords = self._words(d_stream)
+        optr, n_words = self._words(d_out)
+        cw, cwp = _np_u32(codewords)
+        cl, clp = _np_u32(codewordlens)
+        _check(lib().hb_decode(self._ctx, sptr, swords, d_tile_bits.data_ptr(), n_words, cwp, clp, optr,
+                               self._stream()), "hb_decode", self._ctx)
+
     def stitch_seam(self, d_dst, d_src, n_words):
         _check(lib().hb_stitch_seam(self._ctx, d_dst.data_ptr(), d_src.data_ptr(), int(n_words),
                                     self._stream()), "hb_stitch_seam", self._ctx)

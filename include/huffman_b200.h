@@ -200,6 +200,20 @@ HB_API int hb_shard_offsets(const uint64_t *shard_bits, int n_shards, uint64_t *
 HB_API int hb_stitch_seam(hb_ctx *ctx, uint32_t *d_dst, const uint32_t *d_src, uint64_t n_words,
                    void *stream);
 
+/* ---- decoder (no reference equivalent: the reference cannot decode) -----------------
+ * A tile-parallel decoder, so that encode -> decode round trips can be checked on the device at any size.  Not part
+ * of the measured hot path.
+ * hb_encode_tile_index: the bit offset of every encode tile (hb_tile_bytes() of input each) of the LAST job of this
+ * context, n_tiles + 1 device uint64 (the last entry = the end of the stream); call it after hb_encode /
+ * hb_encode_result and before the next encode (the offsets come from the job's look-back tree).
+ * hb_decode: d_stream (stream_words words readable) -> the n_words input words into d_out, bit-exact with the
+ * encoder's input.  The tables must form a prefix code (HB_ERR_CODEWORD otherwise, and when the stream does not
+ * decode tile by tile to exactly the indexed offsets); symbols with length 0 cannot occur.  Synchronises `stream`. */
+HB_API int hb_encode_tile_index(hb_ctx *ctx, uint64_t total_bits, uint64_t *d_tile_bits, void *stream);
+HB_API int hb_decode(hb_ctx *ctx, const uint32_t *d_stream, uint64_t stream_words, const uint64_t *d_tile_bits,
+              uint64_t n_words, const uint32_t codewords[256], const uint32_t codewordlens[256], uint32_t *d_out,
+              void *stream);
+
 /* ---- tooling -----------------------------------------------------------------------------------
  * Deterministic synthetic input generator on the device (the reference's
  * testdatagen.h:62-67 cannot control entropy).  Byte i of the stream, i in [first, first+n):

@@ -429,6 +429,59 @@ def test_repeated_launches_are_deterministic(hb, enc, orc, torch_mod):
             assert int(o[ref_words.size].item()) == 0x5A5A5A5A
 
 
+# ---- decoder (the reference has none): encode -> decode must give the input back ----------
+@pytest.mark.parametrize("skew,nsym", [("geo", 2), ("geo", 22), ("flat", 256), ("fib", 32)])
+@pytest.mark.parametrize("n_bytes", [4, 1028, 32768, 32772, 3 * 32768 + 20, 5 * 1024 * 1024 + 4])
+def test_decode_round_trip(hb, enc, orc, torch_mod, skew, nsym, n_bytes):
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(repr(("dec", skew, nsym, n_bytes)).encode()))
+    h = random_prefix_code(rng, nsym, skew)
+    cw, cl, max_len = hb.build_codebook(h)
+    p = h.astype(np.float64) / float(h.sum())
+    data = rng.choice(256, size=n_bytes, p=p).astype(np.uint8)
+    ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
+    d_in = torch_mod.from_numpy(data).cuda()
+    d_out = torch_mod.full((ref_words.size + 2,), 0x5A5A5A5A, dtype=torch_mod.int32, device="cuda")
+    assert enc.encode(d_in, cw, cl, d_out) == ref_bits
+    n_tiles = (n_bytes + TILE - 1) // TILE
+    d_idx = torch_mod.empty(n_tiles + 1, dtype=torch_mod.int64, device="cuda")
+    enc.tile_index(ref_bits, d_idx)
+    idx = d_idx.cpu().numpy()
+    assert idx[0] == 0 and idx[-1] == ref_bits and np.all(np.diff(idx) >= 0)
+    # every tile offset is the bit count of the symbols before it
+    for t in (1, n_tiles // 2, n_tiles - 1):
+        if 0 < t < n_tiles:
+            assert idx[t] == int(cl.astype(np.uint64)[data[: t * TILE]].sum())
+    d_back = torch_mod.full((n_bytes,), 0xEE, dtype=torch_mod.uint8, device="cuda")
+    enc.decode(d_out[: ref_words.size + 1], d_idx, cw, cl, d_back)
+    assert np.array_equal(d_back.cpu().numpy(), data)
+    # the CPU oracle's bit-serial decoder agrees (an independent decoder of the same stream)
+    if n_bytes <= 200_000:
+        back, end = orc.decode(d_out.cpu().numpy().view(np.uint32), 0, n_bytes, cw, cl)
+        assert end == ref_bits and np.array_equal(back[:n_bytes], data)
+
+
+def test_decode_rejects_foreign_tables(hb, enc, orc, torch_mod):
+    """a stream decoded with another codebook does not end tile by tile at the indexed offsets: HB_ERR_CODEWORD"""
+    rng = np.random.default_rng(3)
+    data = rng.integers(0, 16, size=TILE * 3, dtype=np.uint8)
+    cw, cl, _ = hb.build_codebook(orc.histogram(data))
+    bits_expected = hb.bits_from_hist(orc.histogram(data), cl)
+    d_in = torch_mod.from_numpy(data).cuda()
+    d_out = torch_mod.zeros(bits_expected // 32 + 3, dtype=torch_mod.int32, device="cuda")
+    bits = enc.encode(d_in, cw, cl, d_out)
+    d_idx = torch_mod.empty(4, dtype=torch_mod.int64, device="cuda")
+    enc.tile_index(bits, d_idx)
+    other = rng.integers(0, 16, size=TILE * 3, dtype=np.uint8)
+    other[: TILE] = 3
+    cw2, cl2, _ = hb.build_codebook(orc.histogram(other))
+    assert not np.array_equal(cl, cl2)
+    d_back = torch_mod.empty(data.size, dtype=torch_mod.uint8, device="cuda")
+    with pytest.raises(hb.HBError) as e:
+        enc.decode(d_out, d_idx, cw2, cl2, d_back)
+    assert e.value.status == hb.capi.HB_ERR_CODEWORD
+
+
 # ---- host-buffer entry points (the reference-facing call) ---------------------------------------------------
 def test_vlc_encode_drop_in_signature(hb, orc, ref, c1):
     """hb_vlc_encode(indata, num_elements, outdata, &outsize, codewords, codewordlens), host pointers."""

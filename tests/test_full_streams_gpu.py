@@ -4,6 +4,8 @@
     through the position-sensitive checksums of huffman-gpu_b200/streamsum.py with the stream the UNMODIFIED
     cpu_vlc_encode produced for the same input (tests/golden/streams.json, made by oracle/make_golden_streams.py
     from the CPU generator + oracle/_ref); histogram, codebook and bit count are compared too.
+  * test_round_trip_at_full_size: encode -> hb_decode (the tile-parallel GPU decoder) gives the input back, on the device,
+    for every configuration: a size-independent property that needs no CPU at all.
   * test_whole_stream_word_by_word: C4 (2 GiB) and C5 (8 GiB) once more, this time literally word by word against
     cpu_vlc_encode run live on this box's host (5 s / 21 s of one core), as main_test_cu.cu:170-171 compares.
 Integer work: tolerance zero."""
@@ -86,4 +88,25 @@ def test_whole_stream_word_by_word(hb, ref, name):
     finally:
         enc.close()
         del d_out
+        torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name", ["c2", "t1g", "c3", "c4", "c5"])
+def test_round_trip_at_full_size(hb, name):
+    import torch
+    torch.cuda.set_device(0)
+    enc, d_in, d_out, hist, cw, cl, bits = _encode_whole(hb, torch, name)
+    try:
+        tile = hb.capi.TILE_BYTES
+        n_tiles = (d_in.numel() + tile - 1) // tile
+        d_idx = torch.empty(n_tiles + 1, dtype=torch.int64, device="cuda")
+        enc.tile_index(bits, d_idx)
+        d_back = torch.full((d_in.numel(),), 0xEE, dtype=torch.uint8, device="cuda")
+        enc.decode(d_out[: bits // 32 + 1], d_idx, cw, cl, d_back)
+        step = 1 << 30
+        for lo in range(0, d_in.numel(), step):
+            assert torch.equal(d_back[lo:lo + step], d_in[lo:lo + step]), "decode(encode(x)) != x in GiB %d" % (lo >> 30)
+    finally:
+        enc.close()
+        del d_in, d_out
         torch.cuda.empty_cache()
