@@ -530,6 +530,26 @@ def synth_on_device(hb, enc, torch, wl, n_bytes=None):
     return d
 
 
+def test_encode_host_error_exits_leave_the_context_clean(hb, enc, orc, torch_mod, monkeypatch):
+    """hb_vlc_encode_host with an output that is too small (several chunk launches in flight when the overflow is seen):
+    HB_ERR_CAPACITY, nothing left running or dirty -- the next device-path and host-path jobs on the same context are
+    exact (early returns left launches queued, D2H copies in flight and a stale overflow flag behind)."""
+    monkeypatch.setenv("HB_CHUNK_MIB", "1")
+    rng = np.random.default_rng(21)
+    data = rng.integers(0, 200, size=6 << 20, dtype=np.uint8)
+    cw, cl, _ = hb.build_codebook(orc.histogram(data))
+    ref_words, ref_bits, _ = orc.encode(data.view(np.uint32), cw, cl)
+    small = np.zeros(ref_words.size // 3, dtype=np.uint32)
+    for _ in range(3):
+        with pytest.raises(hb.HBError) as e:
+            enc.encode_host(data.view(np.uint32), cw, cl, small)
+        assert e.value.status == hb.capi.HB_ERR_CAPACITY
+        check_against_oracle(orc, enc, torch_mod, data[: 5 * TILE + 8], cw, cl)      # device path, same context
+        h_out = np.zeros(ref_words.size + 1, dtype=np.uint32)
+        bits, _ = enc.encode_host(data.view(np.uint32), cw, cl, h_out)                # host path, same context
+        assert bits == ref_bits and np.array_equal(h_out[: ref_words.size], ref_words)
+
+
 def test_synth_device_matches_host(hb, enc, orc, torch_mod):
     for name in ("c2", "c3", "c5"):
         wl = hb.workloads.get(name)
