@@ -429,7 +429,8 @@ int hb_stitch_push(hb_comm *c, const uint32_t *d_local, const hb_shard_plan *pla
             const bool seam_last = !(is_last && ((start + bits) & 31u) == 0);   // the zero word has no sharers
             unsigned long long want = (cnt / 4 + 511) / 512;
             if (want < 1) want = 1;
-            const unsigned long long cap = (unsigned long long)c->ctx->sm_count * 4;
+            static const char *env_bps = getenv("HB_STITCH_BLOCKS_PER_SM");          // tuning aid (default 4)
+            const unsigned long long cap = (unsigned long long)c->ctx->sm_count * (env_bps && atoi(env_bps) > 0 ? atoi(env_bps) : 4);
             const unsigned grid = (unsigned)(want < cap ? want : cap);
             stitch_push_kernel<<<grid, 512, 0, st>>>(c->stitch_base + first + skip, words + skip, cnt, d_heads,
                                                      seam_last ? or_lo : 0, seam_last ? or_hi : 0);
