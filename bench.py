@@ -608,6 +608,34 @@ def main():
                                       "not part of `value`"}
             line["stitched_bit_exact"] = exact
             line["parity"]["stitched_stream_vs_cpu_vlc_encode"] = exact
+            # the fused form: every rank encodes STRAIGHT into GPU 0's stream (the encode kernel's copy-out stores go to
+            # peer memory, seam words OR-ed): encode + stitch in one kernel per rank, no local output, no second pass
+            if rank == 0:
+                comm.stitched_view(cap).fill_(0x5A5A5A5A)
+            comm.encode_direct_async(d_in, cw, cl)                     # warm
+            assert comm.encode_result() == my_bits
+            B.barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for _ in range(reps):
+                comm.encode_direct_async(d_in, cw, cl)
+            f1.record()
+            assert comm.encode_result() == my_bits
+            torch.cuda.synchronize()
+            B.barrier()
+            fms = B.max_over_ranks(f0.elapsed_time(f1)) / reps
+            fexact = None
+            if rank == 0 and args.bytes is None:
+                fexact = B.check_sums(args.workload, comm.stitched_view(total_bits // 32 + 1), total_bits, "fused encode+stitch stream")
+            flag = torch.tensor([-1 if fexact is None else int(fexact)], dtype=torch.int64, device="cuda")
+            dist.broadcast(flag, src=0)
+            fexact = None if int(flag[0]) < 0 else bool(int(flag[0]))
+            line["stitch_fused"] = {"ms": fms, "value": total_bytes / (fms * 1e-3) / 1e9, "unit": UNIT,
+                                    "GBps_over_nvlink": moved / (fms * 1e-3) / 1e9, "bit_exact": fexact,
+                                    "what": "hb_shard_encode_direct_async: encode + stitch as ONE kernel per rank (copy-out "
+                                            "stores straight into GPU 0's stream over NVLink); compare with ms_per_step + "
+                                            "stitch.ms for the two-step form"}
+            line["parity"]["fused_stream_vs_cpu_vlc_encode"] = fexact
             comm.stitch_close()
         except Exception as exc:
             line["stitch"] = {"error": repr(exc)}

@@ -58,6 +58,7 @@ SIGNATURES = {
     "hb_stitch_open": (C.c_int, [vp, C.c_uint64, C.c_int, C.POINTER(vp), vp]),
     "hb_stitch_push": (C.c_int, [vp, vp, planp, vp]),
     "hb_stitch_close": (C.c_int, [vp]),
+    "hb_shard_encode_direct_async": (C.c_int, [vp, vp, C.c_uint64, u32p, u32p, planp, vp]),
     "hb_shard_offsets": (C.c_int, [u64p, C.c_int, u64p, u64p]),
     "hb_stitch_seam": (C.c_int, [vp, vp, vp, C.c_uint64, vp]),
     "hb_encode_tile_index": (C.c_int, [vp, C.c_uint64, vp, vp]),

@@ -183,6 +183,7 @@ int launch_tiles(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, uint64_t f
     p.table = ctx->d_table;
     p.result = ctx->h_result + result_slot;
     p.prof = ctx->d_prof;
+    p.seam_flags = ctx->next_seam_flags;
     {
         static const char *pf = getenv("HB_L2_PREFETCH");
         p.l2_prefetch = (pf && atoi(pf) == 0) ? 0u : 1u;    // measured: +1.4 % (1 GiB, H 2.2) .. +2.5 % (H 7.9); $HB_L2_PREFETCH=0 turns it off
@@ -447,6 +448,7 @@ int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const u
     // the last launch's last tile writes result->bits_end; the host touches the block in
     // hb_encode_result only, after the stream has drained.
     if (n_words == 0) {
+        ctx->next_seam_flags = 0;
         // cpuencode.cpp:17 -- the first output word is cleared even for an empty input
         if ((start_bit >> 5) >= out_capacity_words) return HB_ERR_CAPACITY;
         if ((start_bit & 31u) == 0)
@@ -457,6 +459,7 @@ int hb_encode_async(hb_ctx *ctx, const uint32_t *d_in, uint64_t n_words, const u
         return HB_OK;
     }
     rc = launch_tiles(ctx, d_in, n_words, 0, tiles_of(n_words), d_out, out_capacity_words, start_bit, st);
+    ctx->next_seam_flags = 0;
     if (rc != HB_OK) return rc;
     if ((rc = job_launched(ctx, st)) != HB_OK) return rc;
     ctx->pending = true;

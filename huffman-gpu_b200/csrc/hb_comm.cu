@@ -329,6 +329,55 @@ int hb_shard_encode_async(hb_comm *c, const uint32_t *d_in, uint64_t n_words, co
                            local_capacity_words - plan->local_offset_words, plan->phase, stream);
 }
 
+// Fused encode + stitch: the shard is encoded STRAIGHT into the root's stream (the kernel's copy-out stores go to peer
+// memory over NVLink, words already in global phase): no local copy of the output, no second pass.  The two words a shard
+// may share with its neighbours are OR-ed (system-scope reductions) into words the root has zeroed; the kernel leaves
+// the word after a word-aligned end to the next shard.
+int hb_shard_encode_direct_async(hb_comm *c, const uint32_t *d_in, uint64_t n_words, const uint32_t codewords[256],
+                                 const uint32_t codewordlens[256], const hb_shard_plan *plan, void *stream)
+{
+    if (!c || !plan) return HB_ERR_ARG;
+    if (!c->stitch_base || !c->have_plan) return HB_ERR_STATE;
+    Nccl *n = nccl();
+    if (!n) return HB_ERR_NCCL;
+    hb_ctx *ctx = c->ctx;
+    DeviceScope g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int R = c->n_ranks, me = c->rank;
+    unsigned long long *d_mine = c->d_scratch + 512 + HB_MAX_RANKS;
+
+    // the root zeroes every seam word (the first word of a shard that starts mid-word); nobody stores before that
+    if (me == c->stitch_root)
+        for (int r = 0; r < R; r++)
+            if (c->shard_bits[r] && (c->start_bits[r] & 31u))
+                HB_CUDA_C(c, cudaMemsetAsync(c->stitch_base + (c->start_bits[r] >> 5), 0, sizeof(uint32_t), st));
+    HB_CUDA_C(c, cudaMemsetAsync(d_mine, 0, sizeof(unsigned long long), st));
+    HB_NCCL_C(c, n->AllReduce(d_mine, d_mine, 1, ncclUint64, ncclSum, c->comm, st));
+
+    const uint64_t bits = c->shard_bits[me], start = c->start_bits[me];
+    int rc = HB_OK;
+    if (bits) {
+        bool is_last = true;
+        for (int r = me + 1; r < R; r++) is_last = is_last && c->shard_bits[r] == 0;
+        uint32_t flags = 0;
+        if (start & 31u) flags |= hb::kSeamFirst;
+        if (!is_last) flags |= hb::kSeamNoZeroWord | (((start + bits) & 31u) ? hb::kSeamLast : 0u);
+        const uint64_t first = start >> 5;
+        if (first >= c->stitch_words) return HB_ERR_CAPACITY;
+        ctx->next_seam_flags = flags;
+        rc = hb_encode_async(ctx, d_in, n_words, codewords, codewordlens, c->stitch_base + first, c->stitch_words - first,
+                             start & 31u, stream);
+    } else {
+        ctx->pending = true;                   // nothing to write; hb_shard_encode_result reports 0 bits
+        ctx->pending_empty = true;
+        ctx->pending_start_bit = start & 31u;
+    }
+    // completion: the root's stream learns that every rank's kernel (and its peer stores) has ended
+    HB_CUDA_C(c, cudaMemsetAsync(d_mine, 0, sizeof(unsigned long long), st));
+    HB_NCCL_C(c, n->AllReduce(d_mine, d_mine, 1, ncclUint64, ncclSum, c->comm, st));
+    return rc;
+}
+
 int hb_shard_encode_result(hb_comm *c, uint64_t *shard_bits, void *stream)
 {
     if (!c) return HB_ERR_ARG;

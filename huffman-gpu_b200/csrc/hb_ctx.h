@@ -64,6 +64,8 @@ struct hb_ctx {
     uint64_t last_job_tiles = 0, last_job_words = 0, last_job_start_bit = 0;
     bool last_job_valid = false;
 
+    uint32_t next_seam_flags = 0;             // for the next hb_encode_async only (set by hb_shard_encode_direct_async)
+
     unsigned long long *d_prof = nullptr;     // $HB_PROFILE: kernel cycle counters, dumped by hb_free
     uint64_t launches = 0;
     int last_cuda = 0;

@@ -159,6 +159,7 @@ constexpr uint32_t kChunkS = kCtrlS + (uint32_t)offsetof(Ctrl, chunk);
 constexpr uint32_t kRecS = kCtrlS + (uint32_t)offsetof(Ctrl, rec);
 constexpr uint32_t kRecSlow = 0x100u;                   // record flags: leave the fast copy-out
 constexpr uint32_t kRecLast = 0x200u;                   // the job's final chunk (partial word, courtesy zero word)
+constexpr uint32_t kRecFirst = 0x400u;                  // the chunk that owns the job's first output word, which is a shared seam
 
 // position k of a CTA's tile sequence -> slot k % kDepth and mbarrier parity (k / kDepth) & 1
 __device__ __forceinline__ uint32_t slot_of(uint32_t k) { return k & (uint32_t)(kDepth - 1); }
@@ -666,10 +667,12 @@ __device__ void resolver(const EncParams &p, uint32_t tab_s, uint32_t lane, uint
         if (have < 31u) cin |= prev << have;
         const uint32_t nfull = (shw + n) >> 5;                           // output words whose last bit is the chunk's
         const bool last = tile == p.n_tiles - 1 && wk == (uint32_t)kW - 1;
-        const bool slow = last || g0 + nfull > p.out_cap_words;
+        // a shard encoded straight into a shared stream (p.seam_flags): its first word also carries a neighbour's bits
+        const bool first = (p.seam_flags & kSeamFirst) && g0 == (p.start_bit >> 5) && (nfull > 0u || last);
+        const bool slow = last || first || g0 + nfull > p.out_cap_words;
         if (lane < (uint32_t)kW)
             sts_u128(kRecS + (slot * kW + wk) * 16u, (uint32_t)g0, (uint32_t)(g0 >> 32), cin,
-                     shw | (slow ? kRecSlow : 0u) | (last ? kRecLast : 0u));
+                     shw | (slow ? kRecSlow : 0u) | (last ? kRecLast : 0u) | (first ? kRecFirst : 0u));
         __syncwarp();
         if (lane == 0) mbar_arrive(kBarPrefixS + slot * 8u);
         sym = sym_next;
@@ -792,9 +795,19 @@ __device__ __forceinline__ void copy_out(const EncParams &p, uint32_t ring_s, ui
             const uint32_t before =
                 (j == 0) ? rec.z : ((j - 1 < nstage) ? lds_u32(ring_at<SWZ>(ring_s, i0 + j - 1u)) : 0u);
             const uint32_t v = __funnelshift_r(cur, before, sh);
-            if (g0 + j < p.out_cap_words)
-                p.out[g0 + j] = v;
-            else if (!(last && j == nfull && ((sh + n) & 31u) == 0))   // the courtesy zero word may not fit
+            const bool extra = last && j == nfull;                   // the final partial word, or the courtesy zero word
+            const bool zero_word = extra && ((sh + n) & 31u) == 0;
+            // Seams of a shard that is encoded straight into a shared stream (hb_shard_encode_direct_async): its first word
+            // and its final partial word also carry a neighbour's bits -- they are OR-ed into words the root has zeroed --
+            // and the word after a word-aligned end is the next shard's.
+            const bool or_it = ((rec.w & kRecFirst) && j == 0) || (extra && !zero_word && (p.seam_flags & kSeamLast));
+            if (zero_word && (p.seam_flags & kSeamNoZeroWord)) continue;
+            if (g0 + j < p.out_cap_words) {
+                if (or_it)      // system scope: the stream may live on another GPU (peer memory over NVLink)
+                    asm volatile("red.relaxed.sys.global.or.b32 [%0], %1;" ::"l"(p.out + g0 + j), "r"(v) : "memory");
+                else
+                    p.out[g0 + j] = v;
+            } else if (!zero_word)                                   // the courtesy zero word may not fit
                 spill = true;
         }
         if (spill) p.result->overflow = 1ULL;

@@ -55,7 +55,12 @@ struct EncParams {
     EncResult *result;
     unsigned long long *prof;         // optional cycle counters ($HB_PROFILE), else nullptr
     uint32_t l2_prefetch;             // pull the tile after next into L2 (on by default; $HB_L2_PREFETCH=0)
+    uint32_t seam_flags;              // kSeam*: the output is a stream shared with neighbouring shards (hb_comm.cu)
 };
+
+// seam_flags: the first output word is shared with the previous shard (OR it), so is the final partial word with the next
+// (OR it), the word after a word-aligned end belongs to the next shard (do not write the courtesy zero word)
+constexpr uint32_t kSeamFirst = 1u, kSeamLast = 2u, kSeamNoZeroWord = 4u;
 
 // Encode kernel variants.
 //   "packed": table entry = (cw << (32-len)) | len, needs every len <= 24;

@@ -219,6 +219,16 @@ class ShardComm:
         self._ck(lib().hb_stitch_push(self._comm, d_local.data_ptr(), C.byref(plan), self.enc._stream()),
                  "hb_stitch_push")
 
+    def encode_direct_async(self, d_in, cw, cl, plan=None):
+        """fused encode + stitch: the shard goes straight into the root's stream (peer stores from the encode kernel)"""
+        plan = plan or self.plan
+        ptr, n_words = self.enc._words(d_in)
+        cw = np.ascontiguousarray(cw, dtype=np.uint32)
+        cl = np.ascontiguousarray(cl, dtype=np.uint32)
+        self._ck(lib().hb_shard_encode_direct_async(self._comm, ptr, n_words, cw.ctypes.data_as(capi.u32p),
+                                                    cl.ctypes.data_as(capi.u32p), C.byref(plan), self.enc._stream()),
+                 "hb_shard_encode_direct_async")
+
     def stitched_view(self, n_words):
         """root only: the first n_words of the stitched stream as an int32 torch tensor (a view, no copy)"""
         assert self.rank == self.stitch_root and n_words <= self.stitch_cap

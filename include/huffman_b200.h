@@ -190,6 +190,14 @@ HB_API int hb_shard_encode_result(hb_comm *comm, uint64_t *shard_bits, void *str
 HB_API int hb_stitch_open(hb_comm *comm, uint64_t capacity_words, int root, uint32_t **d_stitched, void *stream);
 HB_API int hb_stitch_push(hb_comm *comm, const uint32_t *d_local, const hb_shard_plan *plan, void *stream);
 HB_API int hb_stitch_close(hb_comm *comm);
+/* The fused form of encode + stitch (collective; needs hb_stitch_open): the shard is encoded STRAIGHT into the root's
+ * stream -- the kernel's copy-out stores go to peer memory over NVLink, already in global phase; no local output buffer,
+ * no second pass.  The two words a shard may share with its neighbours are OR-ed into words the root has zeroed.
+ * Asynchronous on `stream`; fetch the bit count with hb_shard_encode_result.  When the root's stream has drained, the
+ * stream is complete. */
+HB_API int hb_shard_encode_direct_async(hb_comm *comm, const uint32_t *d_in, uint64_t n_words,
+                                 const uint32_t codewords[256], const uint32_t codewordlens[256],
+                                 const hb_shard_plan *plan, void *stream);
 
 /* building blocks of the above for callers that bring their own exchange:
  * hb_shard_offsets: exclusive prefix of per-shard bit totals -> start_bit of every shard. */

@@ -164,6 +164,7 @@ def _comm_worker(rank, world, queues, name, n_bytes, ret):
         comm.stitch_open(cap, root=0)
         comm.stitch_push(d_local)
         torch.cuda.synchronize()
+        want_words = want_sums = None
         if rank == 0:
             n = plan.total_bits // 32 + 1
             got_t = comm.stitched_view(n)
@@ -176,6 +177,7 @@ def _comm_worker(rank, world, queues, name, n_bytes, ret):
                 got = got_t.cpu().numpy().view(np.uint32)
                 bad = np.nonzero(got != ref_words[:n])[0]
                 assert bad.size == 0, "first mismatch at word %d of %d" % (bad[0], n)
+                want_words = ref_words
             else:
                 g = json.load(open(os.path.join(ROOT, "tests", "golden", "streams.json")))[name]
                 assert plan.total_bits == g["total_bits"]
@@ -183,6 +185,25 @@ def _comm_worker(rank, world, queues, name, n_bytes, ret):
                 assert np.array_equal(cl, np.array(g["codewordlens"], dtype=np.uint32))
                 sums = stream_sums(got_t, n)
                 assert ["0x%016x" % x for x in sums] == g["sums"], "stitched stream differs from cpu_vlc_encode's"
+                want_sums = g["sums"]
+        # ---- the fused form: every shard encoded STRAIGHT into the root's stream (peer stores from the encode kernel,
+        #      seam words OR-ed into zeroed words); the root's buffer is poisoned first, the result must be the same stream
+        if rank == 0:
+            comm.stitched_view(cap).fill_(0x5A5A5A5A)
+        comm.encode_direct_async(d_in, cw, cl)
+        assert comm.encode_result() == plan.shard_bits
+        torch.cuda.synchronize()
+        if rank == 0:
+            n = plan.total_bits // 32 + 1
+            again = comm.stitched_view(cap)
+            if want_words is not None:
+                got = again[:n].cpu().numpy().view(np.uint32)
+                bad = np.nonzero(got != want_words[:n])[0]
+                assert bad.size == 0, "direct: first mismatch at word %d of %d" % (bad[0], n)
+            else:
+                sums = stream_sums(again, n)
+                assert ["0x%016x" % x for x in sums] == want_sums, "direct: stream differs from cpu_vlc_encode's"
+            assert int(again[n].item()) == 0x5A5A5A5A, "direct: wrote past floor(bits/32)+1 words"
             ret.put("ok")
         comm.stitch_close()
         comm.close()
