@@ -363,10 +363,13 @@ int hb_shard_encode_direct_async(hb_comm *c, const uint32_t *d_in, uint64_t n_wo
         if (start & 31u) flags |= hb::kSeamFirst;
         if (!is_last) flags |= hb::kSeamNoZeroWord | (((start + bits) & 31u) ? hb::kSeamLast : 0u);
         const uint64_t first = start >> 5;
-        if (first >= c->stitch_words) return HB_ERR_CAPACITY;
-        ctx->next_seam_flags = flags;
-        rc = hb_encode_async(ctx, d_in, n_words, codewords, codewordlens, c->stitch_base + first, c->stitch_words - first,
-                             start & 31u, stream);
+        if (first >= c->stitch_words) {
+            rc = HB_ERR_CAPACITY;              // (reported after the closing collective: the other ranks are in it)
+        } else {
+            ctx->next_seam_flags = flags;
+            rc = hb_encode_async(ctx, d_in, n_words, codewords, codewordlens, c->stitch_base + first,
+                                 c->stitch_words - first, start & 31u, stream);
+        }
     } else {
         ctx->pending = true;                   // nothing to write; hb_shard_encode_result reports 0 bits
         ctx->pending_empty = true;
@@ -457,6 +460,7 @@ int hb_stitch_push(hb_comm *c, const uint32_t *d_local, const hb_shard_plan *pla
     // [first, last]; my first word belongs to an earlier rank iff I start mid-word (phase != 0: the bits before mine
     // are somebody's); my last word may be shared with later ranks that start mid-word inside it: I OR their heads in.
     const uint64_t bits = c->shard_bits[me];
+    int rc = HB_OK;
     if (bits) {
         const uint64_t start = c->start_bits[me];
         const uint64_t first = start >> 5, last = (start + bits - 1) >> 5;
@@ -472,8 +476,9 @@ int hb_stitch_push(hb_comm *c, const uint32_t *d_local, const hb_shard_plan *pla
         for (int r = me + 1; r < R; r++) is_last = is_last && c->shard_bits[r] == 0;
         uint64_t n_words = last - first + 1;
         if (is_last && ((start + bits) & 31u) == 0) n_words++;                 // (then `last + 1` is the zero word)
-        if (first + n_words > c->stitch_words) return HB_ERR_CAPACITY;
-        if (n_words > skip) {
+        if (first + n_words > c->stitch_words) {
+            rc = HB_ERR_CAPACITY;              // (reported after the closing collective: the other ranks are in it)
+        } else if (n_words > skip) {
             const uint64_t cnt = n_words - skip;
             const bool seam_last = !(is_last && ((start + bits) & 31u) == 0);   // the zero word has no sharers
             unsigned long long want = (cnt / 4 + 511) / 512;
@@ -491,7 +496,7 @@ int hb_stitch_push(hb_comm *c, const uint32_t *d_local, const hb_shard_plan *pla
     // from a tiny all-reduce queued behind every rank's push
     HB_CUDA_C(c, cudaMemsetAsync(d_mine, 0, sizeof(unsigned long long), st));
     HB_NCCL_C(c, n->AllReduce(d_mine, d_mine, 1, ncclUint64, ncclSum, c->comm, st));
-    return HB_OK;
+    return rc;
 }
 
 int hb_stitch_close(hb_comm *c)
